@@ -111,6 +111,14 @@ int rwkv_b200_forward(rwkv_b200_model *m, const unsigned long long *tokens,
 int rwkv_b200_forward_greedy(rwkv_b200_model *m, unsigned long long token,
                              unsigned long long *next, float *logits_out);
 
+/* Pinned host buffer (max_gpt x 50277 floats) the engine copies logits into; passing
+ * it as `logits_out` avoids one host-side memcpy. This is what RWKV::out points at. */
+float *rwkv_b200_logits_host(rwkv_b200_model *m);
+
+/* Test hook: copy a named device vector ("x", "xs_o", "sr", "xs_v", "xy_new", "dd_new",
+ * "logits") to `dst`. Returns the element count, or -1. */
+long long rwkv_b200_debug_read(rwkv_b200_model *m, const char *name, void *dst, size_t dst_bytes);
+
 /* --- measurement hooks (bench.py); not part of the reference surface ------------ */
 
 /* Decode `n` tokens taken from `tokens` (host array, copied to HBM before timing) on
