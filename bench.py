@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""bench.py — single-stream decode throughput of the B200 RWKV-v4 uint8 engine.
+
+Contract (driver): `python bench.py --gpus N --steps K --warmup W [--impl reference]`
+prints ONE JSON line on rank 0.
+
+  step      one decoded token (one pass of the hot path: 2 + 4*L kernels, + argmax)
+  workload  N=1: RWKV-4 7B shape (L=32, E=4096, uint8) — BASELINE.json's headline config —
+            random-init weights written by tools/genmodel.cpp in the reference's .bin format.
+            N>1: see --workload / DESIGN.md "multi-GPU".
+  value     tokens/s with everything resident in HBM: K graph replays back to back, each =
+            {feed previous argmax, forward, argmax}, CUDA events on the engine stream.
+  e2e       tokens/s through the C-ABI call a user makes (rwkv_b200_forward with HOST token and
+            HOST logits buffer: 32 B H2D + 201,108 B D2H + host argmax every step).
+  roofline  dominant kernel class: algorithmic bytes per launch / mean CUDA-event duration of
+            that class, measured in this process by the engine's launch-by-launch profile run.
+            Weights (7.2 GB) are >> L2 (126 MB), so every launch streams from HBM.
+  cpu_baseline  the CPU oracle (port of the reference CUDA forward) on the host cores, a few
+            tokens of the same model.
+  --impl reference   the UNMODIFIED reference CUDA build (oracle/_ref/ref_harness, compiled from
+            /root/reference by oracle/Makefile) on GPU 0, same .bin, greedy decode through its
+            own RWKV::forward, wall clock — the reference has no CPU forward;
+            its line also carries the oracle's cpu_baseline.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SHAPES = {"169m": (12, 768), "1b5": (24, 2048), "7b": (32, 4096), "14b": (40, 5120)}
+SEED = 20240924
+SEED_TOKEN = 4118
+VOCAB = 50277
+
+
+def algorithmic_bytes_per_token(L, E):
+    """uint8 weights once per token + the small vector terms."""
+    w = 13 * L * E * E + VOCAB * E
+    return w + 4 * (20 * L * E + 2 * E) + 8 * (7 * L * E + 4 * (L + 1) * E) + 64 * L * E + 4 * E + 4 * VOCAB
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu=0):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self.stop_flag, self.proc = gpu, [], False, None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag:
+                    break
+                self.rows.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def model_path(workload, pkg):
+    L, E = SHAPES[workload]
+    base = os.environ.get("RWKV_B200_BENCH_DIR") or ("/dev/shm" if os.path.isdir("/dev/shm") else "/tmp")
+    os.makedirs(base, exist_ok=True)
+    path = os.path.join(base, "rwkv_b200_bench_%s_s%d.bin" % (workload, SEED))
+    if not os.path.exists(path) or os.path.getsize(path) != pkg.build.file_bytes(L, E):
+        tmp = path + ".tmp%d" % os.getpid()
+        pkg.build.genmodel(L, E, SEED, tmp)
+        os.replace(tmp, path)
+    return path
+
+
+def cpu_baseline(path, tokens, budget_s=25.0):
+    """Oracle port on the host cores: a bounded sample of the same decode."""
+    from oracle.oracle import Oracle
+    orc = Oracle(path)
+    n, t_total = 0, 0.0
+    orc.forward(tokens[0])  # first token pages the mmap in; not timed
+    for tok in tokens[1:]:
+        t0 = time.perf_counter()
+        orc.forward(tok)
+        t_total += time.perf_counter() - t0
+        n += 1
+        if t_total > budget_s:
+            break
+    threads = orc.threads
+    orc.close()
+    return {"value": n / t_total if t_total > 0 else 0.0, "unit": "tokens/s", "cores": threads, "kind": "port",
+            "sample": "%d tokens of the same model through oracle/rwkv_oracle.cpp (restatement of rwkv.cu), %d host threads" % (n, threads)}
+
+
+def run_reference(args, pkg, workload):
+    """--impl reference: the unmodified reference CUDA build on GPU 0."""
+    from oracle.oracle import REF_HARNESS
+    L, E = SHAPES[workload]
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    base = {"impl": "reference", "metric": "tokens/sec single-stream decode", "unit": "tokens/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8 weights, f32/f64 math", "data": "synthetic",
+            "config": {"workload": "RWKV-4 %s shape L=%d E=%d uint8, random-init, greedy single-stream decode" % (workload, L, E),
+                       "l2": "weights >> L2, every token streams from HBM"}}
+    if not os.path.exists(REF_HARNESS):
+        base["unavailable"] = "oracle/_ref/ref_harness not built (needs /root/reference at build time)"
+        print(json.dumps(base))
+        return
+    path = model_path(workload, pkg)
+    tf = path + ".seed.txt"
+    with open(tf, "w") as f:
+        f.write("%d\n" % SEED_TOKEN)
+    dump = path + ".refdump"
+    total = args.steps + args.warmup
+    sampler = ClockSampler()
+    sampler.start()
+    r = subprocess.run([REF_HARNESS, path, tf, dump, "--warmup", str(args.warmup), "--dump-every", "0",
+                        "--greedy", str(total)], capture_output=True, text=True)
+    clocks = sampler.finish()
+    res = None
+    for line in r.stdout.splitlines():
+        if line.startswith("REF_RESULT "):
+            res = json.loads(line[len("REF_RESULT "):])
+    if r.returncode != 0 or res is None:
+        base["unavailable"] = "ref_harness failed rc=%d: %s" % (r.returncode, (r.stderr or r.stdout)[-300:].replace("\n", " "))
+        print(json.dumps(base))
+        return
+    toks = [int(x) for x in open(dump + ".tokens").read().split()][:6]
+    cb = cpu_baseline(path, toks or [SEED_TOKEN] * 3, budget_s=20.0)
+    v = res["tokens_per_s"]
+    base.update({"value": v, "ms_per_step": 1000.0 / v if v else None, "clocks": clocks,
+                 "e2e": {"value": v, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                 "cpu_baseline": cb, "gpu_launches": (9 + 20 * L) * args.steps,
+                 "reference_arm": "unmodified /root/reference rwkv.cu + rwkv.h on 1 GPU (its own RWKV::forward incl. its host<->device state copies)"})
+    for p in (dump, dump + ".tokens", tf):
+        try:
+            os.remove(p)
+        except OSError:
+            pass
+    print(json.dumps(base))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=256)
+    ap.add_argument("--warmup", type=int, default=16)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=None, choices=sorted(SHAPES))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    workload = args.workload or "7b"
+    pkg = importlib.import_module("rwkv-cpp-accelerated_b200")
+    pkg.build.build_all(force=False)
+
+    if args.impl == "reference":
+        run_reference(args, pkg, workload)
+        return
+
+    import numpy as np
+    import torch
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    L, E = SHAPES[workload]
+    if rank == 0:
+        path = model_path(workload, pkg)
+    if dist is not None:
+        dist.barrier()
+    path = model_path(workload, pkg)
+    eng = pkg.Engine(path, device=local_rank)
+
+    # ---- warm-up (also builds the CUDA graphs) -------------------------------------------
+    eng.state_zero()
+    eng.decode_timed([SEED_TOKEN] * args.warmup, teacher_forced=False)
+
+    def sync_all():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: device-resident greedy decode --------------------------------------------
+    eng.state_zero()
+    launches0 = eng.launch_count
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    sync_all()
+    ms = eng.decode_timed([SEED_TOKEN] * args.steps, teacher_forced=False)
+    sync_all()
+    launches = eng.launch_count - launches0
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda:%d" % local_rank)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    tokens_total = args.steps * world  # independent streams per rank until the sharded path lands
+    value = tokens_total / (ms / 1e3)
+
+    # ---- e2e: the user-facing call with host buffers -------------------------------------
+    eng.state_zero()
+    tok = SEED_TOKEN
+    for _ in range(args.warmup):
+        tok = int(eng.forward([tok])[0].argmax())
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        tok = int(eng.forward([tok])[0].argmax())
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda:%d" % local_rank)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = tokens_total / float(t.item())
+    clocks = sampler.finish() if rank == 0 else None
+
+    if rank != 0:
+        eng.close()
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- per-kernel roofline (launch-by-launch, CUDA events around every launch) ---------
+    eng.state_zero()
+    prof_tokens = [SEED_TOKEN]
+    tk = SEED_TOKEN
+    for _ in range(7):
+        tk = int(eng.forward([tk])[0].argmax())
+        prof_tokens.append(tk)
+    eng.state_zero()
+    prof = eng.profile(prof_tokens)
+    peak, peak_src = measured_peak()
+    kernels = {}
+    total_ms = sum(v["ms_sum"] for v in prof.values()) or 1.0
+    for name, v in prof.items():
+        if not v["launches"]:
+            continue
+        dur_ms = v["ms_sum"] / v["launches"]
+        kernels[name] = {"launches_per_token": v["launches"] // len(prof_tokens), "us_per_launch": round(dur_ms * 1e3, 3),
+                         "bytes_per_launch": int(v["bytes_per_launch"]),
+                         "gbs": round(v["bytes_per_launch"] / dur_ms / 1e6, 1), "share": round(v["ms_sum"] / total_ms, 4)}
+    dom = max(kernels, key=lambda k: kernels[k]["share"])
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s",
+                "frac": round(kernels[dom]["gbs"] / peak, 4), "traffic": None, "peak_source": peak_src,
+                "how": "algorithmic bytes per launch / mean CUDA-event duration per launch (eager profile run, %d tokens)" % len(prof_tokens)}
+    abytes = algorithmic_bytes_per_token(L, E)
+    cb = None
+    if not args.no_cpu_baseline:
+        cb = cpu_baseline(path, prof_tokens)
+    eng.close()
+
+    out = {
+        "metric": "tokens/sec single-stream decode RWKV-4 7B uint8; achieved HBM GB/s vs peak" if workload == "7b"
+        else "tokens/sec single-stream decode RWKV-4 %s uint8; achieved HBM GB/s vs peak" % workload,
+        "value": round(value, 2), "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(ms / args.steps, 5), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8 weights x 21-bit fixed-point activations (3 int8 limbs, exact int32 accumulate), f64 elementwise",
+        "data": "synthetic",
+        "config": {"workload": "RWKV-4 %s shape (L=%d, E=%d, V=50277) uint8, random-init reference-format .bin, greedy single-stream decode, batch 1" % (workload, L, E),
+                   "l2": "inputs larger than L2: %.2f GB of weights per token vs 126 MB L2" % (abytes / 1e9),
+                   "parallelism": "1 stream per GPU" if world > 1 else "1 GPU"},
+        "hbm": {"algorithmic_bytes_per_token": abytes, "achieved_gbs": round(abytes * (value / world) / 1e9, 1),
+                "frac_of_peak": round(abytes * (value / world) / 1e9 / peak, 4), "peak_gbs": peak, "peak_source": peak_src},
+        "roofline": roofline, "kernels": kernels,
+        "e2e": {"value": round(e2e_value, 2), "unit": "tokens/s", "h2d_bytes_per_step": 32, "d2h_bytes_per_step": VOCAB * 4,
+                "api": "rwkv_b200_forward(model, &token, 1, GPT, host_logits) + host argmax"},
+        "gpu_launches": int(launches), "clocks": clocks, "cpu_baseline": cb,
+    }
+    print(json.dumps(out))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

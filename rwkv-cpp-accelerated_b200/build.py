@@ -99,6 +99,14 @@ def build_all(force=False):
     build_pybind(force)
 
 
+def file_bytes(L, E, V=50277):
+    """Size of a reference-format .bin (include/rwkv/rwkv/format.h: file_bytes)."""
+    f64 = E + 4 * (L + 1) * E + 5 * L * E + E + 3 * L * E + 2 * L * E + 2 * E + 2 * L * E
+    f32 = V * E + V + 2 * E + 6 * L * E + 2 * L * E + (3 * L * E + 2 * L * 4 * E + L * E) + 4 * E + 2 * E
+    u8 = 3 * L * E * E + L * E * E + 2 * L * 4 * E * E + L * E * E + V * E
+    return 16 + 8 * f64 + 4 * f32 + u8
+
+
 def genmodel(n_layers, n_embed, seed, path, threads=None):
     """Write a synthetic reference-format model file (see tools/genmodel.cpp)."""
     build_genmodel()
