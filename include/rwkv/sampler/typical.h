@@ -1,21 +1,25 @@
-// typical.h — locally-typical sampling over the 50277 logits, host side.
+// typical.h — the reference's `typical()` sampler over the 50277 logits, host side.
 //
 // API parity with the reference's include/rwkv/sampler/typical.h:20,60
 //   int typical(float* logits, float temp = 0.9, float tau = 0.8);
 //   std::vector<unsigned long long> typical(int batch, float* logits, float temp, float tau);
 // restated on <random>/<algorithm> (the reference drags in the 58 kLoC NumCpp tree for this).
-// The arithmetic order is the one NumCpp executes, so a default-seeded run draws the same
-// token sequence as the reference:
-//   probs = exp(l) / sum(exp(l))             no max-shift; sequential double accumulation
-//   s_i   = | -log p_i - sum_j(-log p_j * p_j) |      (NaN terms dropped from the sum)
-//   order = stable argsort of s;  cutoff = #{k : cumsum(p[order])_k < tau}
-//   p_i   = 0 where s_i > s[order[cutoff]]
-//   p     = p ^ uint8(1/temp)                the reference's nc::power takes a uint8 exponent
-//                                            (NumCpp/Functions/power.hpp), so 1/0.9 -> 1 and the
-//                                            temperature is a no-op unless temp <= 0.5; temp > 1
-//                                            gives exponent 0, i.e. a uniform draw. Kept as is.
-//   token ~ std::discrete_distribution<int>(p) on one process-wide std::mt19937_64 that is
+//
+// What the reference actually computes (verified by running it: tests/golden/sampler_golden.json
+// holds sequences drawn by the reference binary, and this header reproduces them exactly):
+//   probs = exp(l) / sum(exp(l))        no max-shift; sequential double accumulation
+//   the entropy / argsort / cumulative-tau cutoff is computed but then DISCARDED: the line
+//       probs[shifted_logits > sorted_logits[cutoff]] = 0;          (typical.h:50)
+//     assigns to a temporary, because NumCpp's NdArray::operator[](NdArray<bool>) returns a copy
+//     (NumCpp/NdArray/NdArrayCore.hpp:778). `tau` therefore has no effect;
+//   probs = probs ^ uint8(1/temp)       nc::power takes a uint8 exponent (NumCpp/Functions/power.hpp),
+//                                       so 1/0.9 -> 1 and 1/0.8 -> 1: temperature is a no-op unless
+//                                       temp <= 0.5; temp > 1 gives exponent 0 = a uniform draw;
+//   token ~ std::discrete_distribution<int>(probs) on one process-wide std::mt19937_64 that is
 //           default-seeded (NumCpp/Random/generator.hpp:35).
+// `typical()` keeps exactly that behaviour (results identical to the reference on identical
+// inputs). `typical_filtered()` is the algorithm the reference's own header comment describes
+// (locally typical sampling with a real cutoff and a real temperature) for callers who want it.
 #pragma once
 #include <algorithm>
 #include <cmath>
@@ -32,37 +36,14 @@ inline std::mt19937_64 &rwkv_sampler_generator() {
 
 inline int typical(float *_logits, float _temp = 0.9, float _tau = 0.8) {
     constexpr int len = 50277;
-    std::vector<double> probs(len), surprise(len), shifted(len);
-
+    (void)_tau; // see the header comment: the reference's cutoff never reaches `probs`
+    std::vector<double> probs(len);
     double total = 0.0;
     for (int i = 0; i < len; ++i) {
         probs[i] = std::exp((double)_logits[i]);
         total += probs[i];
     }
     for (int i = 0; i < len; ++i) probs[i] /= total;
-
-    double entropy = 0.0;
-    for (int i = 0; i < len; ++i) {
-        surprise[i] = -std::log(probs[i]);
-        const double term = surprise[i] * probs[i];
-        entropy += std::isnan(term) ? 0.0 : term;
-    }
-    for (int i = 0; i < len; ++i) shifted[i] = std::abs(surprise[i] - entropy);
-
-    std::vector<uint32_t> order(len);
-    std::iota(order.begin(), order.end(), 0u);
-    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return shifted[a] < shifted[b]; });
-
-    const double tau = (double)_tau;
-    int cutoff = 0;
-    double running = 0.0;
-    for (int k = 0; k < len; ++k) {
-        running = (k == 0) ? probs[order[0]] : running + probs[order[k]];
-        if (running < tau) ++cutoff;
-    }
-    const double threshold = shifted[order[std::min(cutoff, len - 1)]];
-    for (int i = 0; i < len; ++i)
-        if (shifted[i] > threshold) probs[i] = 0.0;
 
     if (_temp != 1.0) {
         const uint8_t exponent = (uint8_t)(1.0 / _temp);
@@ -76,7 +57,43 @@ inline int typical(float *_logits, float _temp = 0.9, float _tau = 0.8) {
             probs[i] = v;
         }
     }
+    std::discrete_distribution<int> dist(probs.begin(), probs.end());
+    return dist(rwkv_sampler_generator());
+}
 
+// Locally typical sampling as the reference's header comment (typical.h:1-18) specifies it:
+// keep the tokens whose surprise is closest to the entropy until their mass reaches tau, apply
+// the temperature as probs^(1/temp), sample. Not used by the reference-compatible entry points.
+inline int typical_filtered(const float *_logits, float _temp = 0.9, float _tau = 0.8) {
+    constexpr int len = 50277;
+    std::vector<double> probs(len), shifted(len);
+    double mx = _logits[0];
+    for (int i = 1; i < len; ++i) mx = std::max(mx, (double)_logits[i]);
+    double total = 0.0;
+    for (int i = 0; i < len; ++i) {
+        probs[i] = std::exp((double)_logits[i] - mx);
+        total += probs[i];
+    }
+    double entropy = 0.0;
+    for (int i = 0; i < len; ++i) {
+        probs[i] /= total;
+        if (probs[i] > 0.0) entropy -= probs[i] * std::log(probs[i]);
+    }
+    for (int i = 0; i < len; ++i) shifted[i] = probs[i] > 0.0 ? std::abs(-std::log(probs[i]) - entropy) : INFINITY;
+    std::vector<uint32_t> order(len);
+    std::iota(order.begin(), order.end(), 0u);
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return shifted[a] < shifted[b]; });
+    double running = 0.0;
+    int cutoff = 0;
+    for (int k = 0; k < len; ++k) {
+        running += probs[order[k]];
+        if (running < (double)_tau) ++cutoff;
+    }
+    const double threshold = shifted[order[std::min(cutoff, len - 1)]];
+    for (int i = 0; i < len; ++i) {
+        if (shifted[i] > threshold) probs[i] = 0.0;
+        else if (_temp != 1.0f) probs[i] = std::pow(probs[i], 1.0 / (double)_temp);
+    }
     std::discrete_distribution<int> dist(probs.begin(), probs.end());
     return dist(rwkv_sampler_generator());
 }

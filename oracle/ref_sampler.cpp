@@ -1,0 +1,32 @@
+// ref_sampler.cpp — golden-vector generator: runs the UNMODIFIED reference sampler
+// (include/rwkv/sampler/typical.h + its vendored NumCpp) on synthetic logits.
+// TEST INFRASTRUCTURE, CPU only, built by `make -C oracle ref-tools` into oracle/_ref/.
+//   usage: ref_sampler <n_draws> <temp> <tau> <logit_scale>
+// Logits for draw d: l_i = scale * g(d, i) with g a fixed integer hash mapped to [-1, 1);
+// l_0 = -99 like examples/storygen/storygen.cpp:66. The generator state carries over
+// between draws exactly as in a decode loop. Prints one sampled id per line.
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include "rwkv/sampler/typical.h"
+
+static inline float synth(uint64_t d, uint64_t i, float scale) {
+    uint64_t z = (d * 0x9E3779B97F4A7C15ULL) ^ (i * 0xD6E8FEB86659FD93ULL);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    z ^= z >> 31;
+    return scale * ((float)(z >> 40) * (1.0f / 8388608.0f) - 1.0f);
+}
+int main(int argc, char **argv) {
+    if (argc < 5) return 1;
+    const int n = atoi(argv[1]);
+    const float temp = (float)atof(argv[2]), tau = (float)atof(argv[3]), scale = (float)atof(argv[4]);
+    std::vector<float> logits(50277);
+    for (int d = 0; d < n; ++d) {
+        for (int i = 0; i < 50277; ++i) logits[i] = synth((uint64_t)d, (uint64_t)i, scale);
+        logits[0] = -99.0f;
+        printf("%d\n", typical(logits.data(), temp, tau));
+    }
+    return 0;
+}
