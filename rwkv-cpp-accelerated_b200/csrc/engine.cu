@@ -28,6 +28,7 @@
 #include "../../include/rwkv_b200.h"
 #include "binfmt.h"
 #include "kernels.cuh"
+#include "token_kernel.cuh"
 
 namespace {
 
@@ -51,8 +52,8 @@ int fail(int code, const char *fmt, ...) {
                         __FILE__, __LINE__);                                                       \
     } while (0)
 
-enum KernelClass { K_EMBED = 0, K_ATT_KVR, K_ATT_OUT, K_FFN_RK, K_FFN_V, K_HEAD, K_ARGMAX, K_COUNT };
-const char *kKernelNames[K_COUNT] = {"embed_ln0", "att_kvr", "att_out", "ffn_rk", "ffn_v", "head", "argmax"};
+enum KernelClass { K_EMBED = 0, K_ATT_KVR, K_ATT_OUT, K_FFN_RK, K_FFN_V, K_HEAD, K_ARGMAX, K_TOKEN, K_COUNT };
+const char *kKernelNames[K_COUNT] = {"embed_ln0", "att_kvr", "att_out", "ffn_rk", "ffn_v", "head", "argmax", "token"};
 
 } // namespace
 
@@ -73,6 +74,7 @@ struct rwkv_b200_model {
     unsigned long long *h_next = nullptr;
     // graphs
     bool use_graph = true;
+    bool token_mode = true; // one persistent cooperative kernel per token (default) vs one kernel per phase
     int max_layers = -1; // debug: run only the first n layers
     cudaGraphExec_t g_plain = nullptr, g_greedy = nullptr, g_free = nullptr, g_stream = nullptr;
     const unsigned long long *g_stream_src = nullptr;
@@ -95,6 +97,7 @@ template <class T> int dmalloc(M *m, T **out, size_t count) {
 int layers_to_run(const M *m) { return m->max_layers >= 0 && m->max_layers < (int)m->L ? m->max_layers : (int)m->L; }
 
 unsigned long long kernels_per_token(const M *m, bool greedy) {
+    if (m->token_mode) return 1ull;
     return 2ull + 4ull * layers_to_run(m) + (greedy ? 1 : 0);
 }
 
@@ -105,8 +108,12 @@ template <int CPL> int set_attrs(size_t smem) {
     CK(cudaFuncSetAttribute(rk::k_ffn_rk<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute(rk::k_ffn_v<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute(rk::k_head<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(rk::k_token<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     return 0;
 }
+
+// One cooperative launch = one token (token_kernel.cuh). feed: 0 ctrl->token, 1 ctrl->next, 2 stream.
+template <int CPL> int launch_token_t(rwkv_b200_model *m, int feed, bool greedy, const unsigned long long *stream, cudaStream_t s);
 
 struct EventPair {
     cudaEvent_t a, b;
@@ -158,6 +165,27 @@ int launch_one(M *m, int cls, int layer, cudaStream_t s, Prof *prof) {
     return 0;
 }
 
+template <int CPL> int launch_token_t(M *m, int feed, bool greedy, const unsigned long long *stream, cudaStream_t s) {
+    rk::Params prm = m->p;
+    prm.L_run = layers_to_run(m);
+    prm.feed_mode = feed;
+    prm.greedy = greedy ? 1 : 0;
+    prm.stream = stream;
+    void *args[] = {&prm};
+    CK(cudaLaunchCooperativeKernel((const void *)rk::k_token<CPL>, dim3(m->grid), dim3(rk::kThreads), args, m->smem, s));
+    return 0;
+}
+
+int launch_token(M *m, int feed, bool greedy, const unsigned long long *stream, cudaStream_t s) {
+    switch (m->cpl) {
+    case 2: return launch_token_t<2>(m, feed, greedy, stream, s);
+    case 4: return launch_token_t<4>(m, feed, greedy, stream, s);
+    case 8: return launch_token_t<8>(m, feed, greedy, stream, s);
+    case 10: return launch_token_t<10>(m, feed, greedy, stream, s);
+    default: return fail(3, "unsupported chunks-per-lane %d", m->cpl);
+    }
+}
+
 // The kernel sequence of one token.
 int enqueue_token(M *m, cudaStream_t s, bool greedy, Prof *prof) {
     int rc;
@@ -204,7 +232,10 @@ void drop_graphs(M *m) {
 }
 
 int run_token(M *m, bool greedy) {
-    if (!m->use_graph) {
+    if (m->token_mode) {
+        int rc = launch_token(m, 0, greedy, nullptr, m->stream);
+        if (rc) return rc;
+    } else if (!m->use_graph) {
         int rc = enqueue_token(m, m->stream, greedy, nullptr);
         if (rc) return rc;
     } else {
@@ -330,14 +361,15 @@ int do_load(M *m, const char *path, int quiet) {
     rk::Params &p = m->p;
     p.L = (int)L;
     p.E = (int)E;
-    p.tile_bytes = 40960;
-    p.stages = 4;
+    p.tile_bytes = 20480;
     p.plane_cap = (int)(12 * E);
+    p.stages = (int)std::min<size_t>(rk::kMaxStages, (232448 - rk::smem_bytes(0, 0, p.plane_cap)) / p.tile_bytes);
     p.tp_rank = m->tp_rank;
     p.tp_size = m->tp_size;
     m->smem = rk::smem_bytes(p.stages, p.tile_bytes, p.plane_cap);
     if ((4 * E + m->grid - 1) / m->grid + (E + m->grid - 1) / m->grid + 2 > (unsigned long long)rk::kMaxRowsPerCta ||
-        (E + m->grid - 1) / m->grid + 1 > (unsigned long long)rk::kConsumers ||
+        (E + m->grid - 1) / m->grid + 1 > (unsigned long long)rk::kMaxSlice ||
+        (4 * E + m->grid - 1) / m->grid + 1 > 2ull * rk::kConsumers ||
         (binfmt::kVocab + m->grid - 1) / m->grid + 1 > (unsigned long long)rk::kMaxRowsPerCta ||
         m->grid > rk::kMaxGrid)
         return fail(5, "grid of %d CTAs is too small for n_embed=%llu", m->grid, E);
@@ -420,6 +452,16 @@ int do_load(M *m, const char *path, int quiet) {
         (rc = dmalloc(m, &b3, E)))
         return rc;
     CK(cudaMemsetAsync(p.ctrl, 0, sizeof(rk::Ctrl), m->stream));
+    if ((rc = dmalloc(m, &p.gbar, 64)) || (rc = dmalloc(m, &p.stat_part, 4 * rk::kMaxGrid)) ||
+        (rc = dmalloc(m, &p.vec, 8 * E)) || (rc = dmalloc(m, &p.vpart, 12 * rk::kMaxGrid)) ||
+        (rc = dmalloc(m, &p.amax_val, rk::kMaxGrid)) || (rc = dmalloc(m, &p.amax_idx, rk::kMaxGrid)))
+        return rc;
+    CK(cudaMemsetAsync(p.gbar, 0, 64 * sizeof(unsigned int), m->stream));
+    {
+        int coop = 0;
+        CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, m->device));
+        if (!coop) m->token_mode = false;
+    }
     CK(cudaMemsetAsync(p.x, 0, E * sizeof(double), m->stream));
     m->tensors[X] = p.x;
     m->tensors[STATEXY] = p.sxy; m->tensors[STATEAA] = p.saa; m->tensors[STATEBB] = p.sbb;
@@ -588,7 +630,7 @@ int rwkv_b200_forward(rwkv_b200_model *m, const unsigned long long *tokens, unsi
         c.next = 0;
         c.slot = (mode == RWKV_B200_MODE_PARRALEL) ? t : 0;
         c.pos = 0;
-        CK(cudaMemcpyAsync(m->p.ctrl, &c, sizeof(rk::Ctrl), cudaMemcpyHostToDevice, m->stream));
+        CK(cudaMemcpyAsync(m->p.ctrl, &c, 32, cudaMemcpyHostToDevice, m->stream));
         if ((rc = run_token(m, false))) return rc;
         if (logits_out)
             CK(cudaMemcpyAsync(m->h_logits + t * V, m->p.logits, V * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
@@ -609,7 +651,7 @@ int rwkv_b200_forward_greedy(rwkv_b200_model *m, unsigned long long token, unsig
     c.next = 0;
     c.slot = 0;
     c.pos = 0;
-    CK(cudaMemcpyAsync(m->p.ctrl, &c, sizeof(rk::Ctrl), cudaMemcpyHostToDevice, m->stream));
+    CK(cudaMemcpyAsync(m->p.ctrl, &c, 32, cudaMemcpyHostToDevice, m->stream));
     if ((rc = run_token(m, true))) return rc;
     CK(cudaMemcpyAsync(m->h_next, &m->p.ctrl->next, sizeof(unsigned long long), cudaMemcpyDeviceToHost, m->stream));
     if (logits_out) CK(cudaMemcpyAsync(m->h_logits, m->p.logits, V * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
@@ -633,13 +675,16 @@ int rwkv_b200_decode_timed(rwkv_b200_model *m, const unsigned long long *tokens,
         if (tokens[i] >= binfmt::kVocab) return fail(1, "token id %llu out of range", tokens[i]);
     CK(cudaMalloc((void **)&d_tok, cnt * sizeof(unsigned long long)));
     CK(cudaMemcpy(d_tok, tokens, cnt * sizeof(unsigned long long), cudaMemcpyHostToDevice));
-    rk::Ctrl c{tokens[0], tokens[0], 0, 0};
-    CK(cudaMemcpy(m->p.ctrl, &c, sizeof(c), cudaMemcpyHostToDevice));
+    rk::Ctrl c{tokens[0], tokens[0], 0, 0, 0, {0, 0, 0}};
+    CK(cudaStreamSynchronize(m->stream));
+    CK(cudaMemcpy(m->p.ctrl, &c, 32, cudaMemcpyHostToDevice));
     cudaGraphExec_t g = nullptr;
-    rc = build_graph(m, teacher_forced ? G_STREAM : G_FREE, d_tok, &g);
-    if (rc) {
-        cudaFree(d_tok);
-        return rc;
+    if (!m->token_mode) {
+        rc = build_graph(m, teacher_forced ? G_STREAM : G_FREE, d_tok, &g);
+        if (rc) {
+            cudaFree(d_tok);
+            return rc;
+        }
     }
     cudaEvent_t a, b;
     cudaEventCreate(&a);
@@ -647,16 +692,22 @@ int rwkv_b200_decode_timed(rwkv_b200_model *m, const unsigned long long *tokens,
     cudaStreamSynchronize(m->stream);
     cudaEventRecord(a, m->stream);
     cudaError_t e = cudaSuccess;
-    for (unsigned long long i = 0; i < n && e == cudaSuccess; ++i) e = cudaGraphLaunch(g, m->stream);
+    for (unsigned long long i = 0; i < n && e == cudaSuccess; ++i) {
+        if (m->token_mode) {
+            if (launch_token(m, teacher_forced ? 2 : 1, !teacher_forced, d_tok, m->stream)) e = cudaErrorLaunchFailure;
+        } else {
+            e = cudaGraphLaunch(g, m->stream);
+        }
+    }
     cudaEventRecord(b, m->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);
     if (e == cudaSuccess) cudaEventElapsedTime(ms, a, b);
     cudaEventDestroy(a);
     cudaEventDestroy(b);
-    cudaGraphExecDestroy(g);
+    if (g) cudaGraphExecDestroy(g);
     cudaFree(d_tok);
     if (e != cudaSuccess) return fail(100 + (int)e, "decode_timed failed: %s", cudaGetErrorString(e));
-    m->launches += n * (kernels_per_token(m, !teacher_forced) + 1);
+    m->launches += n * (kernels_per_token(m, !teacher_forced) + (m->token_mode ? 0 : 1));
     return 0;
 }
 
@@ -682,10 +733,30 @@ int rwkv_b200_profile(rwkv_b200_model *m, const unsigned long long *tokens, unsi
     bytes[K_FFN_V] = 4 * E * E + 4 * E * 4 + E * (4 + 16 + 16);
     bytes[K_HEAD] = V * E + E * (8 + 16 + 8) + 4 * V;
     bytes[K_ARGMAX] = 4 * V;
+    bytes[K_TOKEN] = (double)binfmt::algorithmic_bytes_per_token(m->L, m->E);
     for (unsigned long long t = 0; t < n; ++t) {
         if (tokens[t] >= binfmt::kVocab) return fail(1, "token id out of range");
-        rk::Ctrl c{tokens[t], 0, 0, 0};
-        CK(cudaMemcpyAsync(m->p.ctrl, &c, sizeof(c), cudaMemcpyHostToDevice, m->stream));
+        rk::Ctrl c{tokens[t], 0, 0, 0, 0, {0, 0, 0}};
+        if (m->token_mode) {
+            CK(cudaMemcpyAsync(m->p.ctrl, &c, 32, cudaMemcpyHostToDevice, m->stream));
+            cudaEvent_t a, b;
+            CK(cudaEventCreate(&a));
+            CK(cudaEventCreate(&b));
+            CK(cudaStreamSynchronize(m->stream));
+            CK(cudaEventRecord(a, m->stream));
+            if ((rc = launch_token(m, 0, true, nullptr, m->stream))) return rc;
+            CK(cudaEventRecord(b, m->stream));
+            CK(cudaStreamSynchronize(m->stream));
+            float t_ms = 0.f;
+            cudaEventElapsedTime(&t_ms, a, b);
+            cudaEventDestroy(a);
+            cudaEventDestroy(b);
+            ms_sum[K_TOKEN] += t_ms;
+            launches[K_TOKEN] += 1;
+            m->launches += 1;
+            continue;
+        }
+        CK(cudaMemcpyAsync(m->p.ctrl, &c, 32, cudaMemcpyHostToDevice, m->stream));
         CK(cudaStreamSynchronize(m->stream));
         Prof prof;
         rc = enqueue_token(m, m->stream, true, &prof);
@@ -713,6 +784,11 @@ int rwkv_b200_set_option(rwkv_b200_model *m, const char *key, const char *value)
     const std::string k = key;
     const int v = atoi(value);
     if (k == "graph") m->use_graph = v != 0;
+    else if (k == "mode") {
+        if (std::string(value) == "token") m->token_mode = true;
+        else if (std::string(value) == "staged") m->token_mode = false;
+        else return fail(1, "mode must be 'token' or 'staged'");
+    }
     else if (k == "max_layers") m->max_layers = v;
     else if (k == "stages") {
         if (v < 2 || v > rk::kMaxStages) return fail(1, "stages must be 2..%d", rk::kMaxStages);
@@ -722,9 +798,12 @@ int rwkv_b200_set_option(rwkv_b200_model *m, const char *key, const char *value)
         m->smem = smem;
     } else if (k == "tile_bytes") {
         if (v < (int)(4 * m->E) || v % 16) return fail(1, "tile_bytes must be a multiple of 16 and >= 4*n_embed");
-        const size_t smem = rk::smem_bytes(m->p.stages, v, m->p.plane_cap);
+        int st = m->p.stages;
+        while (st > 2 && rk::smem_bytes(st, v, m->p.plane_cap) > 232448) --st;
+        const size_t smem = rk::smem_bytes(st, v, m->p.plane_cap);
         if (smem > 232448) return fail(1, "tile_bytes=%d needs %zu bytes of shared memory", v, smem);
         m->p.tile_bytes = v;
+        m->p.stages = st;
         m->smem = smem;
     } else if (k == "grid") {
         if (v < 1 || v > rk::kMaxGrid) return fail(1, "grid out of range");

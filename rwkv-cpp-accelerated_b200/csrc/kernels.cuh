@@ -36,7 +36,8 @@ constexpr int kVocab = 50277;
 constexpr int kConsumerWarps = 8;
 constexpr int kConsumers = kConsumerWarps * 32; // 256
 constexpr int kThreads = kConsumers + 32;       // + producer warp
-constexpr int kMaxStages = 8;
+constexpr int kMaxStages = 12;
+constexpr int kMaxSlice = 64;        // max elements of the residual stream one CTA owns (token kernel)
 constexpr int kMaxRowsPerCta = 512; // res64 capacity
 constexpr int kMaxGrid = 1024;      // partials capacity
 constexpr int kQMax = (1 << 20) - 1;
@@ -46,6 +47,8 @@ struct Ctrl {
     unsigned long long next;  // argmax of the last logits (forward_greedy)
     unsigned long long slot;  // state slot (PARRALEL mode)
     unsigned long long pos;   // cursor into a device-resident token stream (decode_timed)
+    unsigned int bar_base;    // grid-barrier count at the start of the next token kernel
+    unsigned int pad[3];
 };
 
 // Everything a kernel needs, passed by value (__grid_constant__).
@@ -73,6 +76,17 @@ struct Params {
     double *part_o;                                    // [2][kMaxGrid] max|xs|, sum x*oc  (att_kvr -> att_out)
     double *part_v;                                    // [2][kMaxGrid]                    (ffn_rk  -> ffn_v)
     Ctrl *ctrl;
+    // ---- persistent token kernel (k_token) ------------------------------------------------
+    int L_run;                         // layers to run (debug knob; normally == L)
+    int feed_mode;                     // 0: ctrl->token, 1: ctrl->next (free-running), 2: stream[ctrl->pos]
+    int greedy;                        // 1: finish with an on-device argmax into ctrl->next
+    const unsigned long long *stream;  // device-resident token stream (feed_mode 2)
+    unsigned int *gbar;                // grid barrier counter (monotonic)
+    double *stat_part;                 // [2 parity][2][kMaxGrid]   partial sum(x), sum(x^2) per CTA
+    float *vec;                        // [2 parity][4E]            next-phase activation vector(s), pre-scaled by r
+    double *vpart;                     // [2 parity][3][2][kMaxGrid] per-vector partial max|xs|, sum x*oc per CTA
+    float *amax_val;                   // [kMaxGrid] per-CTA best logit
+    int *amax_idx;                     // [kMaxGrid] and its index
 };
 
 // ---------------------------------------------------------------------------------------
@@ -252,6 +266,8 @@ struct Smem {
     double *scal;        // [8]  S[0..2], off[0..2]
     uint64_t *full;      // [stages]
     uint64_t *empty;     // [stages]
+    double *xown;        // [kMaxSlice] this CTA's slice of the residual stream (token kernel)
+    float *srown;        // [kMaxSlice] sigmoid(ffn r) of the slice
 };
 
 __device__ __forceinline__ Smem carve(uint8_t *base, const Params &p) {
@@ -269,11 +285,16 @@ __device__ __forceinline__ Smem carve(uint8_t *base, const Params &p) {
     s.full = reinterpret_cast<uint64_t *>(q);
     q += kMaxStages * sizeof(uint64_t);
     s.empty = reinterpret_cast<uint64_t *>(q);
+    q += kMaxStages * sizeof(uint64_t);
+    s.xown = reinterpret_cast<double *>(q);
+    q += kMaxSlice * sizeof(double);
+    s.srown = reinterpret_cast<float *>(q);
     return s;
 }
 
 __host__ __device__ inline size_t smem_bytes(int stages, int tile_bytes, int plane_cap) {
-    return (size_t)stages * tile_bytes + plane_cap + kMaxRowsPerCta * 8 + 16 * 8 + 8 * 8 + 2 * kMaxStages * 8 + 128;
+    return (size_t)stages * tile_bytes + plane_cap + kMaxRowsPerCta * 8 + 16 * 8 + 8 * 8 + 2 * kMaxStages * 8 +
+           kMaxSlice * 12 + 128;
 }
 
 // One streamed sub-matrix of a phase: rows [r0, r1) of a row-major int8 matrix with N bytes

@@ -1,0 +1,590 @@
+// token_kernel.cuh — the persistent one-token kernel: one CTA per SM, launched cooperatively,
+// the whole forward of one token in ONE launch.
+//
+// Why (profiles/r01a_staged_ffn_rk_ncu.md): with one kernel per phase, ~45 % of each kernel was the
+// layernorm / token-shift prologue that all 148 CTAs repeated on the same vectors, and the weight
+// stream stopped at every kernel boundary. Here
+//   * each CTA owns a fixed slice of the residual stream (E/grid elements, kept in shared memory
+//     for the whole token) and does the elementwise work for that slice only;
+//   * CTAs exchange the small activation vectors and per-CTA partial reductions through L2, separated
+//     by grid barriers (one monotonic counter, release/acquire at gpu scope);
+//   * the producer warp never waits for a barrier: weights do not depend on activations, so it keeps
+//     filling the shared-memory ring with the NEXT phase's tiles while the consumer warps sit in a
+//     barrier, which keeps HBM busy across phase boundaries.
+//
+// Phase structure per layer (B = grid barrier):
+//   [stats -> LN1 + token shift for own slice] B [gather xk,xv,xr; GEMV K,V,R rows of own channels;
+//   WKV for own channels] B [gather rwkv; GEMV out-proj rows; residual for own slice] B
+//   [stats -> LN2 + token shift for own slice] B [gather xr,xk; GEMV ffn-R rows (own slice) and
+//   ffn-K rows; sigmoid / relu^2] B [gather k4; GEMV ffn-V rows; residual for own slice] B
+// then [stats -> LN_out for own slice] B [gather; head GEMV; logits (+ local argmax)] (B [argmax]).
+//
+// Reference mapping is the same as for the staged kernels in kernels.cuh (rwkv.cu:493-593).
+#pragma once
+#include "kernels.cuh"
+
+namespace rk {
+
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Grid barrier over the consumer threads of all CTAs (the producer warps do not take part).
+__device__ __forceinline__ void grid_sync(unsigned int *bar, unsigned int &target, int ctid) {
+    consumer_sync();
+    target += gridDim.x;
+    if (ctid == 0) {
+        __threadfence();
+        atomicAdd(bar, 1u);
+        unsigned int spins = 0;
+        while ((int)(ld_acquire_u32(bar) - target) < 0) {
+            if (++spins > (1u << 25)) __trap();
+        }
+        __threadfence();
+    }
+    consumer_sync();
+}
+
+// Sum of `a` and sum of `b` over the 256 consumer threads (fixed tree -> deterministic).
+__device__ __forceinline__ void cons_sum2(double &a, double &b, double *scratch, int ctid) {
+    a = warp_sum(a);
+    b = warp_sum(b);
+    const int w = ctid >> 5;
+    consumer_sync();
+    if ((ctid & 31) == 0) {
+        scratch[w] = a;
+        scratch[8 + w] = b;
+    }
+    consumer_sync();
+    double s = 0.0, t = 0.0;
+#pragma unroll
+    for (int i = 0; i < kConsumerWarps; ++i) {
+        s += scratch[i];
+        t += scratch[8 + i];
+    }
+    a = s;
+    b = t;
+}
+
+__device__ __forceinline__ void produce_sub(const Params &p, const Smem &sm, const int8_t *base, int N, int r0, int r1,
+                                            uint32_t &it, uint64_t policy) {
+    int tr = p.tile_bytes / N;
+    if (tr < 1) tr = 1;
+    const uint32_t ring = smem_u32(sm.ring);
+    for (int r = r0; r < r1; r += tr, ++it) {
+        const int rows = min(tr, r1 - r);
+        const uint32_t bytes = (uint32_t)rows * (uint32_t)N;
+        const uint32_t st = it % (uint32_t)p.stages;
+        const uint32_t k = it / (uint32_t)p.stages;
+        if (k > 0) mbar_wait(smem_u32(&sm.empty[st]), (k - 1) & 1);
+        const uint32_t fb = smem_u32(&sm.full[st]);
+        mbar_expect_tx(fb, bytes);
+        bulk_g2s(ring + st * (uint32_t)p.tile_bytes, base + (size_t)r * N, bytes, fb, policy);
+    }
+}
+
+// Consumer side of one streamed sub-matrix. Work units (row, segment) are dealt round-robin to the
+// eight warps across tile boundaries, so tiles may hold any number of rows.
+template <int CPL>
+__device__ __forceinline__ void consume_sub(const Params &p, const Smem &sm, int N, int nseg, int r0, int r1,
+                                            int plane_off, int res_off, uint32_t &it, int warp, int lane) {
+    const int seg_len = N / nseg;
+    const int nchunks = seg_len >> 4;
+    const int seg = warp % nseg;
+    uint4 a0[CPL], a1[CPL], a2[CPL];
+    {
+        const uint32_t pl = smem_u32(sm.planes + plane_off) + (uint32_t)(seg * seg_len);
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) {
+            const int c = lane + 32 * i;
+            if (c < nchunks) {
+                a0[i] = lds128(pl + c * 16);
+                a1[i] = lds128(pl + N + c * 16);
+                a2[i] = lds128(pl + 2 * N + c * 16);
+            } else {
+                a0[i] = a1[i] = a2[i] = make_uint4(0, 0, 0, 0);
+            }
+        }
+    }
+    int tr = p.tile_bytes / N;
+    if (tr < 1) tr = 1;
+    const uint32_t ring = smem_u32(sm.ring);
+    int ubase = 0; // units handed out so far in this sub (mod 8); always a multiple of nseg
+    for (int r = r0; r < r1; r += tr, ++it) {
+        const int rows = min(tr, r1 - r);
+        const uint32_t st = it % (uint32_t)p.stages;
+        const uint32_t k = it / (uint32_t)p.stages;
+        mbar_wait(smem_u32(&sm.full[st]), k & 1);
+        const uint32_t tile = ring + st * (uint32_t)p.tile_bytes;
+        const int units = rows * nseg;
+        for (int u = (warp - ubase) & 7; u < units; u += kConsumerWarps) {
+            const int rl = u / nseg;
+            const uint32_t row = tile + (uint32_t)(rl * N + seg * seg_len);
+            int s0a = 0, s0b = 0, s1a = 0, s1b = 0, s2a = 0, s2b = 0;
+#pragma unroll
+            for (int i = 0; i < CPL; ++i) {
+                const int c = lane + 32 * i;
+                if (c < nchunks) {
+                    const uint4 w = lds128(row + c * 16);
+                    s0a = dp4a_ss(w.x, a0[i].x, s0a);
+                    s1a = dp4a_ss(w.x, a1[i].x, s1a);
+                    s2a = dp4a_ss(w.x, a2[i].x, s2a);
+                    s0b = dp4a_ss(w.y, a0[i].y, s0b);
+                    s1b = dp4a_ss(w.y, a1[i].y, s1b);
+                    s2b = dp4a_ss(w.y, a2[i].y, s2b);
+                    s0a = dp4a_ss(w.z, a0[i].z, s0a);
+                    s1a = dp4a_ss(w.z, a1[i].z, s1a);
+                    s2a = dp4a_ss(w.z, a2[i].z, s2a);
+                    s0b = dp4a_ss(w.w, a0[i].w, s0b);
+                    s1b = dp4a_ss(w.w, a1[i].w, s1b);
+                    s2b = dp4a_ss(w.w, a2[i].w, s2b);
+                }
+            }
+            const int t0 = __reduce_add_sync(0xffffffffu, s0a + s0b);
+            const int t1 = __reduce_add_sync(0xffffffffu, s1a + s1b);
+            const int t2 = __reduce_add_sync(0xffffffffu, s2a + s2b);
+            if (lane == 0) {
+                const long long tot = (((long long)t2 << 7) + (long long)t1) * 128 + (long long)t0;
+                long long *dst = &sm.res64[res_off + (r - r0) + rl];
+                if (nseg == 1) *dst = tot;
+                else atomicAdd(reinterpret_cast<unsigned long long *>(dst), (unsigned long long)tot);
+            }
+        }
+        ubase = (ubase + units) & 7;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&sm.empty[st]));
+    }
+}
+
+// Slice ownership of this CTA.
+struct Slices {
+    int e0, e1, ne; // residual-stream elements / att channels / rows of every E-row matrix
+    int k0, k1, nk; // rows of the 4E-row ffn key matrix
+    int v0, v1, nv; // rows of the head
+};
+__device__ __forceinline__ Slices make_slices(int E) {
+    Slices s;
+    split_rows(E, s.e0, s.e1);
+    s.ne = s.e1 - s.e0;
+    split_rows(4 * E, s.k0, s.k1);
+    s.nk = s.k1 - s.k0;
+    split_rows(kVocab, s.v0, s.v1);
+    s.nv = s.v1 - s.v0;
+    return s;
+}
+
+// The producer's whole-token schedule. MUST enumerate subs in exactly the consumers' order.
+__device__ __forceinline__ void produce_token(const Params &p, const Smem &sm, const Slices &sl) {
+    const uint64_t pol = policy_evict_first();
+    const int E = p.E;
+    uint32_t it = 0;
+    for (int l = 0; l < p.L_run; ++l) {
+        const size_t mo = (size_t)l * E * E;
+        produce_sub(p, sm, p.wk + mo, E, sl.e0, sl.e1, it, pol);
+        produce_sub(p, sm, p.wv + mo, E, sl.e0, sl.e1, it, pol);
+        produce_sub(p, sm, p.wr + mo, E, sl.e0, sl.e1, it, pol);
+        produce_sub(p, sm, p.wo + mo, E, sl.e0, sl.e1, it, pol);
+        produce_sub(p, sm, p.wfr + mo, E, sl.e0, sl.e1, it, pol);
+        produce_sub(p, sm, p.wfk + 4 * mo, E, sl.k0, sl.k1, it, pol);
+        produce_sub(p, sm, p.wfv + 4 * mo, 4 * E, sl.e0, sl.e1, it, pol);
+    }
+    produce_sub(p, sm, p.whead, E, sl.v0, sl.v1, it, pol);
+}
+
+// mean / std of the full residual stream from the per-CTA partial sums, with the reference's f32
+// rounding of the two accumulators (rwkv.cu:412-465, 43-44). sum((x-m)^2) = s2 - 2 m s1 + E m^2.
+__device__ __forceinline__ void stats_from_parts(const Params &p, const double *part, int ctid, double *scratch,
+                                                 double &xmean, double &x2) {
+    double s1 = 0.0, s2 = 0.0;
+    for (int i = ctid; i < (int)gridDim.x; i += kConsumers) {
+        s1 += __ldcg(part + i);
+        s2 += __ldcg(part + kMaxGrid + i);
+    }
+    cons_sum2(s1, s2, scratch, ctid);
+    const double E = (double)p.E;
+    const float mean_acc = (float)s1;
+    const double mean_f = (double)(mean_acc / (float)p.E);
+    double var = s2 - 2.0 * mean_f * s1 + E * mean_f * mean_f;
+    if (var < 0.0) var = 0.0;
+    const float var_acc = (float)var;
+    xmean = (double)mean_acc / E;
+    x2 = (double)sqrtf(var_acc / (float)(p.E - 1));
+}
+
+// Publish this CTA's partial {sum x, sum x^2} of its slice.
+__device__ __forceinline__ void publish_stats(const Smem &sm, double *part, int ne, int ctid) {
+    double s1 = 0.0, s2 = 0.0;
+    if (ctid < ne) {
+        const double v = sm.xown[ctid];
+        s1 = v;
+        s2 = v * v;
+    }
+    cons_sum2(s1, s2, sm.scratch, ctid);
+    if (ctid == 0) {
+        part[blockIdx.x] = s1;
+        part[kMaxGrid + blockIdx.x] = s2;
+    }
+}
+
+// Publish per-vector partial {max |xs|, sum x*oc} of this CTA (nvec <= 3).
+__device__ __forceinline__ void publish_vparts(const Smem &sm, double *vpart, int nvec, double (&mx)[3], double (&of)[3],
+                                               int ctid) {
+    for (int v = 0; v < nvec; ++v) {
+        cons_reduce(of[v], mx[v], sm.scratch, ctid);
+        if (ctid == 0) {
+            vpart[(v * 2 + 0) * kMaxGrid + blockIdx.x] = mx[v];
+            vpart[(v * 2 + 1) * kMaxGrid + blockIdx.x] = of[v];
+        }
+    }
+}
+
+// After a barrier: combine every CTA's partials, read the `nvec` vectors of length N from L2,
+// quantise them into limb planes (vector v at plane offset v*3*N). Leaves S_v and off_v in sm.scal.
+__device__ __forceinline__ void gather_quantise(const Params &p, const Smem &sm, const float *vec, const double *vpart,
+                                                int nvec, int N, int ctid) {
+    double inv[3];
+    for (int v = 0; v < nvec; ++v) {
+        double m = 0.0, s = 0.0;
+        for (int i = ctid; i < (int)gridDim.x; i += kConsumers) {
+            m = fmax(m, __ldcg(vpart + (v * 2 + 0) * kMaxGrid + i));
+            s += __ldcg(vpart + (v * 2 + 1) * kMaxGrid + i);
+        }
+        cons_reduce(s, m, sm.scratch, ctid);
+        inv[v] = m > 0.0 ? (double)kQMax / m : 0.0;
+        if (ctid == 0) {
+            sm.scal[v] = m / (double)kQMax;
+            sm.scal[3 + v] = s;
+        }
+    }
+    const int ng = N >> 2;
+    for (int v = 0; v < nvec; ++v) {
+        const float4 *src = reinterpret_cast<const float4 *>(vec + (size_t)v * N);
+        uint8_t *pl = sm.planes + (size_t)v * 3 * N;
+        for (int g = ctid; g < ng; g += kConsumers) {
+            const float4 f = __ldcg(src + g);
+            const double xs[4] = {(double)f.x, (double)f.y, (double)f.z, (double)f.w};
+            quantize4(xs, inv[v], pl, N, 4 * g);
+        }
+    }
+    consumer_sync();
+}
+
+template <int CPL>
+__global__ void __launch_bounds__(kThreads, 1) k_token(const __grid_constant__ Params p) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    const Smem sm = carve(smem_raw, p);
+    init_barriers(p, sm);
+    const int E = p.E;
+    const Slices sl = make_slices(E);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == kConsumerWarps) {
+        if (lane == 0) produce_token(p, sm, sl);
+        return;
+    }
+    const int ctid = threadIdx.x;
+    const int ne = sl.ne, nk = sl.nk;
+    const bool mine = ctid < ne;      // this thread owns residual element j
+    const int j = sl.e0 + (mine ? ctid : 0);
+    Ctrl *ctrl = p.ctrl;
+    unsigned int target = ctrl->bar_base;
+    unsigned long long token = ctrl->token;
+    if (p.feed_mode == 1) token = ctrl->next;
+    else if (p.feed_mode == 2) token = p.stream[ctrl->pos];
+    const size_t so = (size_t)ctrl->slot * p.L * E; // state slot offset
+    unsigned int q = 0;                              // exchange-buffer parity counter (one per barrier)
+    uint32_t it = 0;
+    auto statp = [&](unsigned int qq) { return p.stat_part + (size_t)(qq & 1) * 2 * kMaxGrid; };
+    auto vecp = [&](unsigned int qq) { return p.vec + (size_t)(qq & 1) * 4 * E; };
+    auto vpartp = [&](unsigned int qq) { return p.vpart + (size_t)(qq & 1) * 6 * kMaxGrid; };
+
+    // ---- x = LN0(emb[token]) for the own slice (rwkv.cu:513-524) --------------------------------
+    {
+        const float *row = p.emb + (size_t)token * E;
+        auto loadx = [&](int g, double (&v)[4]) {
+            const float4 f = *reinterpret_cast<const float4 *>(row + 4 * g);
+            v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+        };
+        double xmean, x2;
+        ln_stats(E, ctid, sm.scratch, loadx, xmean, x2);
+        if (mine) sm.xown[ctid] = p.ln[j] * (((double)row[j] - xmean) / x2) + p.ln[E + j];
+        publish_stats(sm, statp(q), ne, ctid); // (cons_sum2 inside orders the xown writes)
+    }
+    // parameters of the first LN1 / token-shift slice computation
+    double lw = 0, lb = 0, mk = 0, mv = 0, mr = 0, st = 0;
+    float rk = 0, rv = 0, rr = 0, ok = 0, ov = 0, orr = 0;
+    auto prefetch_att = [&](int l) {
+        if (mine) {
+            const size_t lo = (size_t)l * E + j;
+            lw = p.ln[(size_t)(4 * l + 2) * E + j];
+            lb = p.ln[(size_t)(4 * l + 3) * E + j];
+            mk = p.mixk[lo]; mv = p.mixv[lo]; mr = p.mixr[lo];
+            rk = p.rk[lo]; rv = p.rv[lo]; rr = p.rr[lo];
+            ok = p.ock[lo]; ov = p.ocv[lo]; orr = p.ocr[lo];
+            st = p.sxy[so + lo];
+        }
+    };
+    if (p.L_run > 0) prefetch_att(0);
+    grid_sync(p.gbar, target, ctid);
+    ++q;
+
+    for (int l = 0; l < p.L_run; ++l) {
+        const size_t lo = (size_t)l * E;
+        // ======== LN1 + token shift for the own slice (rwkv.cu:535-540) ==========================
+        {
+            double xmean, x2;
+            stats_from_parts(p, statp(q - 1), ctid, sm.scratch, xmean, x2);
+            double mx[3] = {0, 0, 0}, of[3] = {0, 0, 0};
+            if (mine) {
+                const double ln = lw * ((sm.xown[ctid] - xmean) / x2) + lb;
+                const float fk = (float)(mk * ln + (1.0 - mk) * st);
+                const float fv = (float)(mv * ln + (1.0 - mv) * st);
+                const float fr = (float)(mr * ln + (1.0 - mr) * st);
+                const float xk = (float)((double)fk * (double)rk);
+                const float xv = (float)((double)fv * (double)rv);
+                const float xr = (float)((double)fr * (double)rr);
+                float *vec = vecp(q);
+                vec[j] = xk;
+                vec[E + j] = xv;
+                vec[2 * E + j] = xr;
+                mx[0] = fabs((double)xk); mx[1] = fabs((double)xv); mx[2] = fabs((double)xr);
+                of[0] = (double)fk * (double)ok; of[1] = (double)fv * (double)ov; of[2] = (double)fr * (double)orr;
+                p.sxy[so + lo + j] = ln; // only the owner ever reads or writes this element
+            }
+            publish_vparts(sm, vpartp(q), 3, mx, of, ctid);
+        }
+        grid_sync(p.gbar, target, ctid);
+        ++q;
+        // ======== K, V, R GEMVs for the own channels + WKV (rwkv.cu:542-545) =====================
+        gather_quantise(p, sm, vecp(q - 1), vpartp(q - 1), 3, E, ctid);
+        {
+            double aa = 0, bb = 0, wd = 0, ub = 0;
+            float ro = 0, oco = 0;
+            if (mine) {
+                aa = p.saa[so + lo + j];
+                bb = p.sbb[so + lo + j];
+                wd = p.decay[lo + j];
+                ub = p.bonus[lo + j];
+                ro = p.ro[lo + j];
+                oco = p.oco[lo + j];
+            }
+            const size_t mo = (size_t)l * E * E;
+            (void)mo;
+            consume_sub<CPL>(p, sm, E, 1, sl.e0, sl.e1, 0, 0, it, warp, lane);
+            consume_sub<CPL>(p, sm, E, 1, sl.e0, sl.e1, 3 * E, ne, it, warp, lane);
+            consume_sub<CPL>(p, sm, E, 1, sl.e0, sl.e1, 6 * E, 2 * ne, it, warp, lane);
+            consumer_sync();
+            double mx[3] = {0, 0, 0}, of[3] = {0, 0, 0};
+            if (mine) {
+                const float kf = (float)(sm.scal[0] * (double)sm.res64[ctid] + sm.scal[3]);
+                const float vf = (float)(sm.scal[1] * (double)sm.res64[ne + ctid] + sm.scal[4]);
+                const float rf = (float)(sm.scal[2] * (double)sm.res64[2 * ne + ctid] + sm.scal[5]);
+                const double vv = (double)vf;
+                const double e1 = exp(ub + wd + (double)kf);
+                double y = (aa + e1 * vv) / (bb + e1);
+                y = (1.0 / (1.0 + (double)expf(-rf))) * y;
+                const double ek = exp((double)kf), ew = exp(wd);
+                p.saa[so + lo + j] = (aa + ek * vv) * ew;
+                p.sbb[so + lo + j] = (bb + ek) * ew;
+                const float rw = (float)y;
+                const float xo = (float)((double)rw * (double)ro);
+                vecp(q)[j] = xo;
+                mx[0] = fabs((double)xo);
+                of[0] = (double)rw * (double)oco;
+            }
+            publish_vparts(sm, vpartp(q), 1, mx, of, ctid);
+        }
+        grid_sync(p.gbar, target, ctid);
+        ++q;
+        // ======== out-projection + residual (rwkv.cu:548-553) =====================================
+        gather_quantise(p, sm, vecp(q - 1), vpartp(q - 1), 1, E, ctid);
+        // parameters of the LN2 / ffn token-shift slice computation (used two barriers later)
+        double flw = 0, flb = 0, fmk = 0, fmr = 0, fst = 0;
+        float frr = 0, frk = 0, forr = 0, fok = 0;
+        if (mine) {
+            flw = p.ln[(size_t)(4 * (l + 1)) * E + j];
+            flb = p.ln[(size_t)(4 * (l + 1) + 1) * E + j];
+            fmk = p.fmixk[lo + j]; fmr = p.fmixr[lo + j];
+            frr = p.rfr[lo + j]; frk = p.rfk[lo + j];
+            forr = p.ocfr[lo + j]; fok = p.ocfk[lo + j];
+            fst = p.sdd[so + lo + j];
+        }
+        consume_sub<CPL>(p, sm, E, 1, sl.e0, sl.e1, 0, 0, it, warp, lane);
+        consumer_sync();
+        if (mine) {
+            const float y = (float)(sm.scal[0] * (double)sm.res64[ctid] + sm.scal[3]);
+            const float xf = (float)sm.xown[ctid] + y;
+            sm.xown[ctid] = (double)xf;
+        }
+        publish_stats(sm, statp(q), ne, ctid);
+        grid_sync(p.gbar, target, ctid);
+        ++q;
+        // ======== LN2 + token shift for the own slice (rwkv.cu:557-562) ===========================
+        {
+            double xmean, x2;
+            stats_from_parts(p, statp(q - 1), ctid, sm.scratch, xmean, x2);
+            double mx[3] = {0, 0, 0}, of[3] = {0, 0, 0};
+            if (mine) {
+                const double ln = flw * ((sm.xown[ctid] - xmean) / x2) + flb;
+                const float fr = (float)(fmr * ln + (1.0 - fmr) * fst);
+                const float fk = (float)(fmk * ln + (1.0 - fmk) * fst);
+                const float xr = (float)((double)fr * (double)frr);
+                const float xk = (float)((double)fk * (double)frk);
+                float *vec = vecp(q);
+                vec[j] = xr;
+                vec[E + j] = xk;
+                mx[0] = fabs((double)xr); mx[1] = fabs((double)xk);
+                of[0] = (double)fr * (double)forr; of[1] = (double)fk * (double)fok;
+                p.sdd[so + lo + j] = ln;
+            }
+            publish_vparts(sm, vpartp(q), 2, mx, of, ctid);
+        }
+        grid_sync(p.gbar, target, ctid);
+        ++q;
+        // ======== ffn R (own slice rows) and ffn K (4E rows) + sigmoid / relu^2 (rwkv.cu:566-573) ==
+        gather_quantise(p, sm, vecp(q - 1), vpartp(q - 1), 2, E, ctid);
+        {
+            float rvk[2] = {0, 0}, ovk[2] = {0, 0}; // ffn-V scale / offset of the own K rows (<= 2 per thread)
+            const float *rvp = p.rfv + (size_t)l * 4 * E, *ovp = p.ocfv + (size_t)l * 4 * E;
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                const int i = ctid + t * kConsumers;
+                if (i < nk) {
+                    rvk[t] = rvp[sl.k0 + i];
+                    ovk[t] = ovp[sl.k0 + i];
+                }
+            }
+            consume_sub<CPL>(p, sm, E, 1, sl.e0, sl.e1, 0, 0, it, warp, lane);
+            consume_sub<CPL>(p, sm, E, 1, sl.k0, sl.k1, 3 * E, ne, it, warp, lane);
+            consumer_sync();
+            if (mine) {
+                const float y = (float)(sm.scal[0] * (double)sm.res64[ctid] + sm.scal[3]);
+                sm.srown[ctid] = (float)(1.0 / (1.0 + exp(-(double)y)));
+            }
+            double mx[3] = {0, 0, 0}, of[3] = {0, 0, 0};
+            float *vec = vecp(q);
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                const int i = ctid + t * kConsumers;
+                if (i < nk) {
+                    float a = (float)(sm.scal[1] * (double)sm.res64[ne + i] + sm.scal[4]);
+                    a = a > 0.0f ? a : 0.0f;
+                    a = a * a;
+                    const float xv = (float)((double)a * (double)rvk[t]);
+                    vec[sl.k0 + i] = xv;
+                    mx[0] = fmax(mx[0], (double)xv);
+                    of[0] += (double)a * (double)ovk[t];
+                }
+            }
+            publish_vparts(sm, vpartp(q), 1, mx, of, ctid);
+        }
+        grid_sync(p.gbar, target, ctid);
+        ++q;
+        // ======== ffn V (rows of 4E bytes, four warps per row) + residual (rwkv.cu:574-577) =========
+        zero_res(sm, ne, ctid);
+        gather_quantise(p, sm, vecp(q - 1), vpartp(q - 1), 1, 4 * E, ctid);
+        if (l + 1 < p.L_run) prefetch_att(l + 1);
+        consume_sub<CPL>(p, sm, 4 * E, 4, sl.e0, sl.e1, 0, 0, it, warp, lane);
+        consumer_sync();
+        if (mine) {
+            const float kv = (float)(sm.scal[0] * (double)sm.res64[ctid] + sm.scal[3]);
+            sm.xown[ctid] = sm.xown[ctid] + (double)(kv * sm.srown[ctid]);
+        }
+        publish_stats(sm, statp(q), ne, ctid);
+        grid_sync(p.gbar, target, ctid);
+        ++q;
+    }
+
+    // ======== LN_out for the own slice, head GEMV (rwkv.cu:585-589) ================================
+    {
+        double xmean, x2;
+        stats_from_parts(p, statp(q - 1), ctid, sm.scratch, xmean, x2);
+        double mx[3] = {0, 0, 0}, of[3] = {0, 0, 0};
+        if (mine) {
+            const double *lwp = p.ln + (size_t)(4 * p.L + 2) * E;
+            const float f = (float)(lwp[j] * ((sm.xown[ctid] - xmean) / x2) + lwp[E + j]);
+            const float xh = (float)((double)f * (double)p.rhead[j]);
+            vecp(q)[j] = xh;
+            mx[0] = fabs((double)xh);
+            of[0] = (double)f * (double)p.ochead[j];
+            p.x[j] = sm.xown[ctid]; // residual stream after the last layer (debug / tests)
+        }
+        publish_vparts(sm, vpartp(q), 1, mx, of, ctid);
+    }
+    grid_sync(p.gbar, target, ctid);
+    ++q;
+    gather_quantise(p, sm, vecp(q - 1), vpartp(q - 1), 1, E, ctid);
+    consume_sub<CPL>(p, sm, E, 1, sl.v0, sl.v1, 0, 0, it, warp, lane);
+    consumer_sync();
+    {
+        float best = -INFINITY;
+        int bidx = 0x7fffffff;
+        for (int i = ctid; i < sl.nv; i += kConsumers) {
+            const float y = (float)(sm.scal[0] * (double)sm.res64[i] + sm.scal[3]);
+            p.logits[sl.v0 + i] = y;
+            if (y > best) { // i ascending per thread: first maximum kept
+                best = y;
+                bidx = sl.v0 + i;
+            }
+        }
+        if (p.greedy) {
+            // block arg-max, first index wins ties
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov2 = __shfl_xor_sync(0xffffffffu, best, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+                if (ov2 > best || (ov2 == best && oi < bidx)) {
+                    best = ov2;
+                    bidx = oi;
+                }
+            }
+            float *bv = reinterpret_cast<float *>(sm.scratch);
+            int *bi = reinterpret_cast<int *>(sm.scratch + 8);
+            consumer_sync();
+            if (lane == 0) {
+                bv[warp] = best;
+                bi[warp] = bidx;
+            }
+            consumer_sync();
+            if (ctid == 0) {
+                for (int w = 1; w < kConsumerWarps; ++w)
+                    if (bv[w] > best || (bv[w] == best && bi[w] < bidx)) {
+                        best = bv[w];
+                        bidx = bi[w];
+                    }
+                p.amax_val[blockIdx.x] = best;
+                p.amax_idx[blockIdx.x] = bidx;
+            }
+            grid_sync(p.gbar, target, ctid);
+            if (blockIdx.x == 0 && warp == 0) {
+                float b2 = -INFINITY;
+                int i2 = 0x7fffffff;
+                for (int c = lane; c < (int)gridDim.x; c += 32) {
+                    const float v = __ldcg(p.amax_val + c);
+                    const int ix = __ldcg(p.amax_idx + c);
+                    if (v > b2 || (v == b2 && ix < i2)) {
+                        b2 = v;
+                        i2 = ix;
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float ov2 = __shfl_xor_sync(0xffffffffu, b2, o);
+                    const int oi = __shfl_xor_sync(0xffffffffu, i2, o);
+                    if (ov2 > b2 || (ov2 == b2 && oi < i2)) {
+                        b2 = ov2;
+                        i2 = oi;
+                    }
+                }
+                if (lane == 0) ctrl->next = (unsigned long long)(i2 == 0x7fffffff ? 0 : i2);
+            }
+        }
+    }
+    if (blockIdx.x == 0 && ctid == 0) {
+        ctrl->bar_base = target;
+        if (p.feed_mode == 2) ctrl->pos = ctrl->pos + 1;
+    }
+}
+
+} // namespace rk
