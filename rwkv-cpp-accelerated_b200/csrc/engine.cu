@@ -108,7 +108,8 @@ template <int CPL> int set_attrs(size_t smem) {
     CK(cudaFuncSetAttribute(rk::k_ffn_rk<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute(rk::k_ffn_v<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute(rk::k_head<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CK(cudaFuncSetAttribute(rk::k_token<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(rk::k_token<CPL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(rk::k_token<CPL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     return 0;
 }
 
@@ -172,7 +173,8 @@ template <int CPL> int launch_token_t(M *m, int feed, bool greedy, const unsigne
     prm.greedy = greedy ? 1 : 0;
     prm.stream = stream;
     void *args[] = {&prm};
-    CK(cudaLaunchCooperativeKernel((const void *)rk::k_token<CPL>, dim3(m->grid), dim3(rk::kThreads), args, m->smem, s));
+    const void *fn = (m->E == (unsigned long long)CPL * 512) ? (const void *)rk::k_token<CPL, true> : (const void *)rk::k_token<CPL, false>;
+    CK(cudaLaunchCooperativeKernel(fn, dim3(m->grid), dim3(rk::kTokThreads), args, m->smem, s));
     return 0;
 }
 

@@ -266,6 +266,7 @@ struct Smem {
     double *scal;        // [8]  S[0..2], off[0..2]
     uint64_t *full;      // [stages]
     uint64_t *empty;     // [stages]
+    double *red;         // [2][6][8] alternating reduction scratch (token kernel)
     double *xown;        // [kMaxSlice] this CTA's slice of the residual stream (token kernel)
     float *srown;        // [kMaxSlice] sigmoid(ffn r) of the slice
 };
@@ -286,6 +287,8 @@ __device__ __forceinline__ Smem carve(uint8_t *base, const Params &p) {
     q += kMaxStages * sizeof(uint64_t);
     s.empty = reinterpret_cast<uint64_t *>(q);
     q += kMaxStages * sizeof(uint64_t);
+    s.red = reinterpret_cast<double *>(q);
+    q += 96 * sizeof(double);
     s.xown = reinterpret_cast<double *>(q);
     q += kMaxSlice * sizeof(double);
     s.srown = reinterpret_cast<float *>(q);
@@ -294,7 +297,7 @@ __device__ __forceinline__ Smem carve(uint8_t *base, const Params &p) {
 
 __host__ __device__ inline size_t smem_bytes(int stages, int tile_bytes, int plane_cap) {
     return (size_t)stages * tile_bytes + plane_cap + kMaxRowsPerCta * 8 + 16 * 8 + 8 * 8 + 2 * kMaxStages * 8 +
-           kMaxSlice * 12 + 128;
+           96 * 8 + kMaxSlice * 12 + 128;
 }
 
 // One streamed sub-matrix of a phase: rows [r0, r1) of a row-major int8 matrix with N bytes

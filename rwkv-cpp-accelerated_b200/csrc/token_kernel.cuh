@@ -36,70 +36,104 @@ __device__ __forceinline__ void grid_sync(unsigned int *bar, unsigned int &targe
     consumer_sync();
     target += gridDim.x;
     if (ctid == 0) {
-        __threadfence();
-        atomicAdd(bar, 1u);
+        // release: everything this CTA wrote (ordered before by the bar.sync above) is visible to any
+        // thread that observes the increment with an acquire load.
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
         unsigned int spins = 0;
         while ((int)(ld_acquire_u32(bar) - target) < 0) {
             if (++spins > (1u << 25)) __trap();
         }
-        __threadfence();
     }
     consumer_sync();
 }
 
-// Sum of `a` and sum of `b` over the 256 consumer threads (fixed tree -> deterministic).
-__device__ __forceinline__ void cons_sum2(double &a, double &b, double *scratch, int ctid) {
-    a = warp_sum(a);
-    b = warp_sum(b);
+// Multi-value block reductions over the 256 consumer threads with ONE named-barrier each: the
+// scratch area alternates between two buffers, so a reduction never overwrites values that
+// slower threads of the previous reduction may still be reading.
+struct Red {
+    double *buf;
+    int par;
+};
+template <int NS, int NM>
+__device__ __forceinline__ void cons_multi(double *s, double *m, Red &rd, int ctid) {
+    static_assert(NS + NM <= 6, "reduction scratch holds six values");
     const int w = ctid >> 5;
-    consumer_sync();
-    if ((ctid & 31) == 0) {
-        scratch[w] = a;
-        scratch[8 + w] = b;
-    }
-    consumer_sync();
-    double s = 0.0, t = 0.0;
+    double *b = rd.buf + rd.par * 48;
 #pragma unroll
-    for (int i = 0; i < kConsumerWarps; ++i) {
-        s += scratch[i];
-        t += scratch[8 + i];
+    for (int k = 0; k < NS; ++k) {
+        s[k] = warp_sum(s[k]);
+        if ((ctid & 31) == 0) b[k * 8 + w] = s[k];
     }
-    a = s;
-    b = t;
+#pragma unroll
+    for (int k = 0; k < NM; ++k) {
+        m[k] = warp_max(m[k]);
+        if ((ctid & 31) == 0) b[(NS + k) * 8 + w] = m[k];
+    }
+    consumer_sync();
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+        double t = 0.0;
+#pragma unroll
+        for (int i = 0; i < kConsumerWarps; ++i) t += b[k * 8 + i];
+        s[k] = t;
+    }
+#pragma unroll
+    for (int k = 0; k < NM; ++k) {
+        double t = b[(NS + k) * 8];
+#pragma unroll
+        for (int i = 1; i < kConsumerWarps; ++i) t = fmax(t, b[(NS + k) * 8 + i]);
+        m[k] = t;
+    }
+    rd.par ^= 1;
 }
+
+// Position in the shared-memory ring: stage index + parity of the current pass over the ring.
+struct RingPos {
+    uint32_t stage, phase;
+    __device__ __forceinline__ void advance(uint32_t stages) {
+        if (++stage == stages) {
+            stage = 0;
+            phase ^= 1;
+        }
+    }
+};
 
 __device__ __forceinline__ void produce_sub(const Params &p, const Smem &sm, const int8_t *base, int N, int r0, int r1,
-                                            uint32_t &it, uint64_t policy) {
+                                            RingPos &rp, uint64_t policy) {
     int tr = p.tile_bytes / N;
     if (tr < 1) tr = 1;
     const uint32_t ring = smem_u32(sm.ring);
-    for (int r = r0; r < r1; r += tr, ++it) {
+    const uint32_t full0 = smem_u32(sm.full), empty0 = smem_u32(sm.empty);
+    for (int r = r0; r < r1; r += tr) {
         const int rows = min(tr, r1 - r);
         const uint32_t bytes = (uint32_t)rows * (uint32_t)N;
-        const uint32_t st = it % (uint32_t)p.stages;
-        const uint32_t k = it / (uint32_t)p.stages;
-        if (k > 0) mbar_wait(smem_u32(&sm.empty[st]), (k - 1) & 1);
-        const uint32_t fb = smem_u32(&sm.full[st]);
+        // first pass over the ring: a fresh mbarrier reports the "previous" phase as complete
+        mbar_wait(empty0 + 8 * rp.stage, rp.phase ^ 1);
+        const uint32_t fb = full0 + 8 * rp.stage;
         mbar_expect_tx(fb, bytes);
-        bulk_g2s(ring + st * (uint32_t)p.tile_bytes, base + (size_t)r * N, bytes, fb, policy);
+        bulk_g2s(ring + rp.stage * (uint32_t)p.tile_bytes, base + (size_t)r * N, bytes, fb, policy);
+        rp.advance((uint32_t)p.stages);
     }
 }
 
 // Consumer side of one streamed sub-matrix. Work units (row, segment) are dealt round-robin to the
-// eight warps across tile boundaries, so tiles may hold any number of rows.
-template <int CPL>
-__device__ __forceinline__ void consume_sub(const Params &p, const Smem &sm, int N, int nseg, int r0, int r1,
-                                            int plane_off, int res_off, uint32_t &it, int warp, int lane) {
-    const int seg_len = N / nseg;
+// eight warps across tile boundaries, so tiles may hold any number of rows. NSEG == 1: one warp
+// per row, exact row total -> res64[res_off + row]; NSEG == 4 (rows of 4E bytes): four warps per
+// row, one E-byte segment each, segment totals -> res64[res_off + row*4 + seg] (summed by the
+// epilogue; no atomics).
+template <int CPL, bool FULL, int NSEG>
+__device__ __forceinline__ void consume_sub(const Params &p, const Smem &sm, int N, int r0, int r1, int plane_off,
+                                            int res_off, RingPos &rp, int warp, int lane) {
+    const int seg_len = N / NSEG;
     const int nchunks = seg_len >> 4;
-    const int seg = warp % nseg;
+    const int seg = warp % NSEG;
     uint4 a0[CPL], a1[CPL], a2[CPL];
     {
         const uint32_t pl = smem_u32(sm.planes + plane_off) + (uint32_t)(seg * seg_len);
 #pragma unroll
         for (int i = 0; i < CPL; ++i) {
             const int c = lane + 32 * i;
-            if (c < nchunks) {
+            if (FULL || c < nchunks) {
                 a0[i] = lds128(pl + c * 16);
                 a1[i] = lds128(pl + N + c * 16);
                 a2[i] = lds128(pl + 2 * N + c * 16);
@@ -111,50 +145,52 @@ __device__ __forceinline__ void consume_sub(const Params &p, const Smem &sm, int
     int tr = p.tile_bytes / N;
     if (tr < 1) tr = 1;
     const uint32_t ring = smem_u32(sm.ring);
-    int ubase = 0; // units handed out so far in this sub (mod 8); always a multiple of nseg
-    for (int r = r0; r < r1; r += tr, ++it) {
+    const uint32_t full0 = smem_u32(sm.full), empty0 = smem_u32(sm.empty);
+    const uint32_t lane_off = (uint32_t)(seg * seg_len + lane * 16);
+    int ubase = 0; // units handed out so far in this sub (mod 8); always a multiple of NSEG
+    for (int r = r0; r < r1; r += tr) {
         const int rows = min(tr, r1 - r);
-        const uint32_t st = it % (uint32_t)p.stages;
-        const uint32_t k = it / (uint32_t)p.stages;
-        mbar_wait(smem_u32(&sm.full[st]), k & 1);
-        const uint32_t tile = ring + st * (uint32_t)p.tile_bytes;
-        const int units = rows * nseg;
+        mbar_wait(full0 + 8 * rp.stage, rp.phase);
+        const uint32_t tile = ring + rp.stage * (uint32_t)p.tile_bytes + lane_off;
+        const int units = rows * NSEG;
         for (int u = (warp - ubase) & 7; u < units; u += kConsumerWarps) {
-            const int rl = u / nseg;
-            const uint32_t row = tile + (uint32_t)(rl * N + seg * seg_len);
+            const int rl = u / NSEG;
+            const uint32_t row = tile + (uint32_t)(rl * N);
+            // all loads of the row segment first, then the arithmetic: keeps CPL 128-bit LDS in flight
+            uint4 w[CPL];
+#pragma unroll
+            for (int i = 0; i < CPL; ++i) {
+                if (FULL || lane + 32 * i < nchunks) w[i] = lds128(row + i * 512);
+                else w[i] = make_uint4(0, 0, 0, 0);
+            }
             int s0a = 0, s0b = 0, s1a = 0, s1b = 0, s2a = 0, s2b = 0;
 #pragma unroll
             for (int i = 0; i < CPL; ++i) {
-                const int c = lane + 32 * i;
-                if (c < nchunks) {
-                    const uint4 w = lds128(row + c * 16);
-                    s0a = dp4a_ss(w.x, a0[i].x, s0a);
-                    s1a = dp4a_ss(w.x, a1[i].x, s1a);
-                    s2a = dp4a_ss(w.x, a2[i].x, s2a);
-                    s0b = dp4a_ss(w.y, a0[i].y, s0b);
-                    s1b = dp4a_ss(w.y, a1[i].y, s1b);
-                    s2b = dp4a_ss(w.y, a2[i].y, s2b);
-                    s0a = dp4a_ss(w.z, a0[i].z, s0a);
-                    s1a = dp4a_ss(w.z, a1[i].z, s1a);
-                    s2a = dp4a_ss(w.z, a2[i].z, s2a);
-                    s0b = dp4a_ss(w.w, a0[i].w, s0b);
-                    s1b = dp4a_ss(w.w, a1[i].w, s1b);
-                    s2b = dp4a_ss(w.w, a2[i].w, s2b);
-                }
+                s0a = dp4a_ss(w[i].x, a0[i].x, s0a);
+                s1a = dp4a_ss(w[i].x, a1[i].x, s1a);
+                s2a = dp4a_ss(w[i].x, a2[i].x, s2a);
+                s0b = dp4a_ss(w[i].y, a0[i].y, s0b);
+                s1b = dp4a_ss(w[i].y, a1[i].y, s1b);
+                s2b = dp4a_ss(w[i].y, a2[i].y, s2b);
+                s0a = dp4a_ss(w[i].z, a0[i].z, s0a);
+                s1a = dp4a_ss(w[i].z, a1[i].z, s1a);
+                s2a = dp4a_ss(w[i].z, a2[i].z, s2a);
+                s0b = dp4a_ss(w[i].w, a0[i].w, s0b);
+                s1b = dp4a_ss(w[i].w, a1[i].w, s1b);
+                s2b = dp4a_ss(w[i].w, a2[i].w, s2b);
             }
             const int t0 = __reduce_add_sync(0xffffffffu, s0a + s0b);
             const int t1 = __reduce_add_sync(0xffffffffu, s1a + s1b);
             const int t2 = __reduce_add_sync(0xffffffffu, s2a + s2b);
             if (lane == 0) {
                 const long long tot = (((long long)t2 << 7) + (long long)t1) * 128 + (long long)t0;
-                long long *dst = &sm.res64[res_off + (r - r0) + rl];
-                if (nseg == 1) *dst = tot;
-                else atomicAdd(reinterpret_cast<unsigned long long *>(dst), (unsigned long long)tot);
+                sm.res64[res_off + ((r - r0) + rl) * NSEG + seg] = tot;
             }
         }
         ubase = (ubase + units) & 7;
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&sm.empty[st]));
+        if (lane == 0) mbar_arrive(empty0 + 8 * rp.stage);
+        rp.advance((uint32_t)p.stages);
     }
 }
 
@@ -179,34 +215,34 @@ __device__ __forceinline__ Slices make_slices(int E) {
 __device__ __forceinline__ void produce_token(const Params &p, const Smem &sm, const Slices &sl) {
     const uint64_t pol = policy_evict_first();
     const int E = p.E;
-    uint32_t it = 0;
+    RingPos rp{0, 0};
     for (int l = 0; l < p.L_run; ++l) {
         const size_t mo = (size_t)l * E * E;
-        produce_sub(p, sm, p.wk + mo, E, sl.e0, sl.e1, it, pol);
-        produce_sub(p, sm, p.wv + mo, E, sl.e0, sl.e1, it, pol);
-        produce_sub(p, sm, p.wr + mo, E, sl.e0, sl.e1, it, pol);
-        produce_sub(p, sm, p.wo + mo, E, sl.e0, sl.e1, it, pol);
-        produce_sub(p, sm, p.wfr + mo, E, sl.e0, sl.e1, it, pol);
-        produce_sub(p, sm, p.wfk + 4 * mo, E, sl.k0, sl.k1, it, pol);
-        produce_sub(p, sm, p.wfv + 4 * mo, 4 * E, sl.e0, sl.e1, it, pol);
+        produce_sub(p, sm, p.wk + mo, E, sl.e0, sl.e1, rp, pol);
+        produce_sub(p, sm, p.wv + mo, E, sl.e0, sl.e1, rp, pol);
+        produce_sub(p, sm, p.wr + mo, E, sl.e0, sl.e1, rp, pol);
+        produce_sub(p, sm, p.wo + mo, E, sl.e0, sl.e1, rp, pol);
+        produce_sub(p, sm, p.wfr + mo, E, sl.e0, sl.e1, rp, pol);
+        produce_sub(p, sm, p.wfk + 4 * mo, E, sl.k0, sl.k1, rp, pol);
+        produce_sub(p, sm, p.wfv + 4 * mo, 4 * E, sl.e0, sl.e1, rp, pol);
     }
-    produce_sub(p, sm, p.whead, E, sl.v0, sl.v1, it, pol);
+    produce_sub(p, sm, p.whead, E, sl.v0, sl.v1, rp, pol);
 }
 
 // mean / std of the full residual stream from the per-CTA partial sums, with the reference's f32
 // rounding of the two accumulators (rwkv.cu:412-465, 43-44). sum((x-m)^2) = s2 - 2 m s1 + E m^2.
-__device__ __forceinline__ void stats_from_parts(const Params &p, const double *part, int ctid, double *scratch,
-                                                 double &xmean, double &x2) {
-    double s1 = 0.0, s2 = 0.0;
+__device__ __forceinline__ void stats_from_parts(const Params &p, const double *part, int ctid, Red &rd, double &xmean,
+                                                 double &x2) {
+    double s[2] = {0.0, 0.0};
     for (int i = ctid; i < (int)gridDim.x; i += kConsumers) {
-        s1 += __ldcg(part + i);
-        s2 += __ldcg(part + kMaxGrid + i);
+        s[0] += __ldcg(part + i);
+        s[1] += __ldcg(part + kMaxGrid + i);
     }
-    cons_sum2(s1, s2, scratch, ctid);
+    cons_multi<2, 0>(s, nullptr, rd, ctid);
     const double E = (double)p.E;
-    const float mean_acc = (float)s1;
+    const float mean_acc = (float)s[0];
     const double mean_f = (double)(mean_acc / (float)p.E);
-    double var = s2 - 2.0 * mean_f * s1 + E * mean_f * mean_f;
+    double var = s[1] - 2.0 * mean_f * s[0] + E * mean_f * mean_f;
     if (var < 0.0) var = 0.0;
     const float var_acc = (float)var;
     xmean = (double)mean_acc / E;
@@ -214,77 +250,109 @@ __device__ __forceinline__ void stats_from_parts(const Params &p, const double *
 }
 
 // Publish this CTA's partial {sum x, sum x^2} of its slice.
-__device__ __forceinline__ void publish_stats(const Smem &sm, double *part, int ne, int ctid) {
-    double s1 = 0.0, s2 = 0.0;
+__device__ __forceinline__ void publish_stats(const Smem &sm, double *part, int ne, Red &rd, int ctid) {
+    double s[2] = {0.0, 0.0};
     if (ctid < ne) {
         const double v = sm.xown[ctid];
-        s1 = v;
-        s2 = v * v;
+        s[0] = v;
+        s[1] = v * v;
     }
-    cons_sum2(s1, s2, sm.scratch, ctid);
+    cons_multi<2, 0>(s, nullptr, rd, ctid);
     if (ctid == 0) {
-        part[blockIdx.x] = s1;
-        part[kMaxGrid + blockIdx.x] = s2;
+        part[blockIdx.x] = s[0];
+        part[kMaxGrid + blockIdx.x] = s[1];
     }
 }
 
-// Publish per-vector partial {max |xs|, sum x*oc} of this CTA (nvec <= 3).
-__device__ __forceinline__ void publish_vparts(const Smem &sm, double *vpart, int nvec, double (&mx)[3], double (&of)[3],
-                                               int ctid) {
-    for (int v = 0; v < nvec; ++v) {
-        cons_reduce(of[v], mx[v], sm.scratch, ctid);
-        if (ctid == 0) {
+// Publish per-vector partial {max |xs|, sum x*oc} of this CTA.
+template <int NVEC>
+__device__ __forceinline__ void publish_vparts(double *vpart, double *mx, double *of, Red &rd, int ctid) {
+    cons_multi<NVEC, NVEC>(of, mx, rd, ctid);
+    if (ctid == 0) {
+#pragma unroll
+        for (int v = 0; v < NVEC; ++v) {
             vpart[(v * 2 + 0) * kMaxGrid + blockIdx.x] = mx[v];
             vpart[(v * 2 + 1) * kMaxGrid + blockIdx.x] = of[v];
         }
     }
 }
 
-// After a barrier: combine every CTA's partials, read the `nvec` vectors of length N from L2,
-// quantise them into limb planes (vector v at plane offset v*3*N). Leaves S_v and off_v in sm.scal.
-__device__ __forceinline__ void gather_quantise(const Params &p, const Smem &sm, const float *vec, const double *vpart,
-                                                int nvec, int N, int ctid) {
-    double inv[3];
-    for (int v = 0; v < nvec; ++v) {
-        double m = 0.0, s = 0.0;
+// After a barrier: ONE L2 round trip fetches every CTA's partials and the NVEC activation vectors
+// (length N each, NG float4 groups per thread), then one block reduction, then quantisation from
+// registers into the limb planes (vector v at plane offset v*3*N). Leaves S_v / off_v in sm.scal.
+template <int NVEC, int NG>
+__device__ __forceinline__ void gather_quantise(const Smem &sm, const float *vec, const double *vpart, int N, Red &rd,
+                                                int ctid) {
+    double m[NVEC], s[NVEC];
+    float4 f[NVEC][NG];
+    const int ng = N >> 2;
+#pragma unroll
+    for (int v = 0; v < NVEC; ++v) {
+        m[v] = 0.0;
+        s[v] = 0.0;
         for (int i = ctid; i < (int)gridDim.x; i += kConsumers) {
-            m = fmax(m, __ldcg(vpart + (v * 2 + 0) * kMaxGrid + i));
-            s += __ldcg(vpart + (v * 2 + 1) * kMaxGrid + i);
-        }
-        cons_reduce(s, m, sm.scratch, ctid);
-        inv[v] = m > 0.0 ? (double)kQMax / m : 0.0;
-        if (ctid == 0) {
-            sm.scal[v] = m / (double)kQMax;
-            sm.scal[3 + v] = s;
+            m[v] = fmax(m[v], __ldcg(vpart + (v * 2 + 0) * kMaxGrid + i));
+            s[v] += __ldcg(vpart + (v * 2 + 1) * kMaxGrid + i);
         }
     }
-    const int ng = N >> 2;
-    for (int v = 0; v < nvec; ++v) {
+#pragma unroll
+    for (int v = 0; v < NVEC; ++v) {
         const float4 *src = reinterpret_cast<const float4 *>(vec + (size_t)v * N);
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+            const int idx = ctid + kConsumers * g;
+            f[v][g] = idx < ng ? __ldcg(src + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    cons_multi<NVEC, NVEC>(s, m, rd, ctid);
+#pragma unroll
+    for (int v = 0; v < NVEC; ++v) {
+        const double inv = m[v] > 0.0 ? (double)kQMax / m[v] : 0.0;
+        if (ctid == 0) {
+            sm.scal[v] = m[v] / (double)kQMax;
+            sm.scal[3 + v] = s[v];
+        }
         uint8_t *pl = sm.planes + (size_t)v * 3 * N;
-        for (int g = ctid; g < ng; g += kConsumers) {
-            const float4 f = __ldcg(src + g);
-            const double xs[4] = {(double)f.x, (double)f.y, (double)f.z, (double)f.w};
-            quantize4(xs, inv[v], pl, N, 4 * g);
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+            const int idx = ctid + kConsumers * g;
+            if (idx < ng) {
+                const double xs[4] = {(double)f[v][g].x, (double)f[v][g].y, (double)f[v][g].z, (double)f[v][g].w};
+                quantize4(xs, inv, pl, N, 4 * idx);
+            }
         }
     }
     consumer_sync();
 }
 
-template <int CPL>
-__global__ void __launch_bounds__(kThreads, 1) k_token(const __grid_constant__ Params p) {
+// Thread layout of the token kernel: two consumer warpgroups (warps 0-7) + one producer warpgroup
+// (warp 8 streams weights, warps 9-11 only donate their registers). With 384 threads the compiler
+// budget is 168 registers/thread; `setmaxnreg` then moves the producer warpgroup's share to the
+// consumers (40 vs 232), which is what lets ptxas keep CPL 128-bit LDS in flight next to the
+// CPL*12 limb registers without spilling.
+constexpr int kTokThreads = 384;
+constexpr int kProducerRegs = 40;
+constexpr int kConsumerRegs = 232;
+
+// CPL: 16-byte chunks per lane; FULL: n_embed == CPL*512, i.e. no lane is ever out of range.
+template <int CPL, bool FULL>
+__global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant__ Params p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const Smem sm = carve(smem_raw, p);
     init_barriers(p, sm);
     const int E = p.E;
     const Slices sl = make_slices(E);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (warp == kConsumerWarps) {
-        if (lane == 0) produce_token(p, sm, sl);
+    if (warp >= kConsumerWarps) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kProducerRegs));
+        if (warp == kConsumerWarps && lane == 0) produce_token(p, sm, sl);
         return;
     }
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kConsumerRegs));
+    constexpr int GROUPS = (CPL + 1) / 2; // float4 groups per thread for a vector of length E
     const int ctid = threadIdx.x;
     const int ne = sl.ne, nk = sl.nk;
+    Red rd{sm.red, 0};
     const bool mine = ctid < ne;      // this thread owns residual element j
     const int j = sl.e0 + (mine ? ctid : 0);
     Ctrl *ctrl = p.ctrl;
@@ -294,7 +362,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_token(const __grid_constant__ P
     else if (p.feed_mode == 2) token = p.stream[ctrl->pos];
     const size_t so = (size_t)ctrl->slot * p.L * E; // state slot offset
     unsigned int q = 0;                              // exchange-buffer parity counter (one per barrier)
-    uint32_t it = 0;
+    RingPos rp{0, 0};
     auto statp = [&](unsigned int qq) { return p.stat_part + (size_t)(qq & 1) * 2 * kMaxGrid; };
     auto vecp = [&](unsigned int qq) { return p.vec + (size_t)(qq & 1) * 4 * E; };
     auto vpartp = [&](unsigned int qq) { return p.vpart + (size_t)(qq & 1) * 6 * kMaxGrid; };
@@ -309,7 +377,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_token(const __grid_constant__ P
         double xmean, x2;
         ln_stats(E, ctid, sm.scratch, loadx, xmean, x2);
         if (mine) sm.xown[ctid] = p.ln[j] * (((double)row[j] - xmean) / x2) + p.ln[E + j];
-        publish_stats(sm, statp(q), ne, ctid); // (cons_sum2 inside orders the xown writes)
+        publish_stats(sm, statp(q), ne, rd, ctid);
     }
     // parameters of the first LN1 / token-shift slice computation
     double lw = 0, lb = 0, mk = 0, mv = 0, mr = 0, st = 0;
@@ -334,7 +402,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_token(const __grid_constant__ P
         // ======== LN1 + token shift for the own slice (rwkv.cu:535-540) ==========================
         {
             double xmean, x2;
-            stats_from_parts(p, statp(q - 1), ctid, sm.scratch, xmean, x2);
+            stats_from_parts(p, statp(q - 1), ctid, rd, xmean, x2);
             double mx[3] = {0, 0, 0}, of[3] = {0, 0, 0};
             if (mine) {
                 const double ln = lw * ((sm.xown[ctid] - xmean) / x2) + lb;
@@ -352,12 +420,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_token(const __grid_constant__ P
                 of[0] = (double)fk * (double)ok; of[1] = (double)fv * (double)ov; of[2] = (double)fr * (double)orr;
                 p.sxy[so + lo + j] = ln; // only the owner ever reads or writes this element
             }
-            publish_vparts(sm, vpartp(q), 3, mx, of, ctid);
+            publish_vparts<3>(vpartp(q), mx, of, rd, ctid);
         }
         grid_sync(p.gbar, target, ctid);
         ++q;
         // ======== K, V, R GEMVs for the own channels + WKV (rwkv.cu:542-545) =====================
-        gather_quantise(p, sm, vecp(q - 1), vpartp(q - 1), 3, E, ctid);
+        gather_quantise<3, GROUPS>(sm, vecp(q - 1), vpartp(q - 1), E, rd, ctid);
         {
             double aa = 0, bb = 0, wd = 0, ub = 0;
             float ro = 0, oco = 0;
@@ -371,9 +439,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_token(const __grid_constant__ P
             }
             const size_t mo = (size_t)l * E * E;
             (void)mo;
-            consume_sub<CPL>(p, sm, E, 1, sl.e0, sl.e1, 0, 0, it, warp, lane);
-            consume_sub<CPL>(p, sm, E, 1, sl.e0, sl.e1, 3 * E, ne, it, warp, lane);
-            consume_sub<CPL>(p, sm, E, 1, sl.e0, sl.e1, 6 * E, 2 * ne, it, warp, lane);
+            consume_sub<CPL, FULL, 1>(p, sm, E, sl.e0, sl.e1, 0, 0, rp, warp, lane);
+            consume_sub<CPL, FULL, 1>(p, sm, E, sl.e0, sl.e1, 3 * E, ne, rp, warp, lane);
+            consume_sub<CPL, FULL, 1>(p, sm, E, sl.e0, sl.e1, 6 * E, 2 * ne, rp, warp, lane);
             consumer_sync();
             double mx[3] = {0, 0, 0}, of[3] = {0, 0, 0};
             if (mine) {
@@ -393,12 +461,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_token(const __grid_constant__ P
                 mx[0] = fabs((double)xo);
                 of[0] = (double)rw * (double)oco;
             }
-            publish_vparts(sm, vpartp(q), 1, mx, of, ctid);
+            publish_vparts<1>(vpartp(q), mx, of, rd, ctid);
         }
         grid_sync(p.gbar, target, ctid);
         ++q;
         // ======== out-projection + residual (rwkv.cu:548-553) =====================================
-        gather_quantise(p, sm, vecp(q - 1), vpartp(q - 1), 1, E, ctid);
+        gather_quantise<1, GROUPS>(sm, vecp(q - 1), vpartp(q - 1), E, rd, ctid);
         // parameters of the LN2 / ffn token-shift slice computation (used two barriers later)
         double flw = 0, flb = 0, fmk = 0, fmr = 0, fst = 0;
         float frr = 0, frk = 0, forr = 0, fok = 0;
@@ -410,20 +478,20 @@ __global__ void __launch_bounds__(kThreads, 1) k_token(const __grid_constant__ P
             forr = p.ocfr[lo + j]; fok = p.ocfk[lo + j];
             fst = p.sdd[so + lo + j];
         }
-        consume_sub<CPL>(p, sm, E, 1, sl.e0, sl.e1, 0, 0, it, warp, lane);
+        consume_sub<CPL, FULL, 1>(p, sm, E, sl.e0, sl.e1, 0, 0, rp, warp, lane);
         consumer_sync();
         if (mine) {
             const float y = (float)(sm.scal[0] * (double)sm.res64[ctid] + sm.scal[3]);
             const float xf = (float)sm.xown[ctid] + y;
             sm.xown[ctid] = (double)xf;
         }
-        publish_stats(sm, statp(q), ne, ctid);
+        publish_stats(sm, statp(q), ne, rd, ctid);
         grid_sync(p.gbar, target, ctid);
         ++q;
         // ======== LN2 + token shift for the own slice (rwkv.cu:557-562) ===========================
         {
             double xmean, x2;
-            stats_from_parts(p, statp(q - 1), ctid, sm.scratch, xmean, x2);
+            stats_from_parts(p, statp(q - 1), ctid, rd, xmean, x2);
             double mx[3] = {0, 0, 0}, of[3] = {0, 0, 0};
             if (mine) {
                 const double ln = flw * ((sm.xown[ctid] - xmean) / x2) + flb;
@@ -438,12 +506,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_token(const __grid_constant__ P
                 of[0] = (double)fr * (double)forr; of[1] = (double)fk * (double)fok;
                 p.sdd[so + lo + j] = ln;
             }
-            publish_vparts(sm, vpartp(q), 2, mx, of, ctid);
+            publish_vparts<2>(vpartp(q), mx, of, rd, ctid);
         }
         grid_sync(p.gbar, target, ctid);
         ++q;
         // ======== ffn R (own slice rows) and ffn K (4E rows) + sigmoid / relu^2 (rwkv.cu:566-573) ==
-        gather_quantise(p, sm, vecp(q - 1), vpartp(q - 1), 2, E, ctid);
+        gather_quantise<2, GROUPS>(sm, vecp(q - 1), vpartp(q - 1), E, rd, ctid);
         {
             float rvk[2] = {0, 0}, ovk[2] = {0, 0}; // ffn-V scale / offset of the own K rows (<= 2 per thread)
             const float *rvp = p.rfv + (size_t)l * 4 * E, *ovp = p.ocfv + (size_t)l * 4 * E;
@@ -455,8 +523,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_token(const __grid_constant__ P
                     ovk[t] = ovp[sl.k0 + i];
                 }
             }
-            consume_sub<CPL>(p, sm, E, 1, sl.e0, sl.e1, 0, 0, it, warp, lane);
-            consume_sub<CPL>(p, sm, E, 1, sl.k0, sl.k1, 3 * E, ne, it, warp, lane);
+            consume_sub<CPL, FULL, 1>(p, sm, E, sl.e0, sl.e1, 0, 0, rp, warp, lane);
+            consume_sub<CPL, FULL, 1>(p, sm, E, sl.k0, sl.k1, 3 * E, ne, rp, warp, lane);
             consumer_sync();
             if (mine) {
                 const float y = (float)(sm.scal[0] * (double)sm.res64[ctid] + sm.scal[3]);
@@ -477,21 +545,21 @@ __global__ void __launch_bounds__(kThreads, 1) k_token(const __grid_constant__ P
                     of[0] += (double)a * (double)ovk[t];
                 }
             }
-            publish_vparts(sm, vpartp(q), 1, mx, of, ctid);
+            publish_vparts<1>(vpartp(q), mx, of, rd, ctid);
         }
         grid_sync(p.gbar, target, ctid);
         ++q;
         // ======== ffn V (rows of 4E bytes, four warps per row) + residual (rwkv.cu:574-577) =========
-        zero_res(sm, ne, ctid);
-        gather_quantise(p, sm, vecp(q - 1), vpartp(q - 1), 1, 4 * E, ctid);
+        gather_quantise<1, 4 * GROUPS>(sm, vecp(q - 1), vpartp(q - 1), 4 * E, rd, ctid);
         if (l + 1 < p.L_run) prefetch_att(l + 1);
-        consume_sub<CPL>(p, sm, 4 * E, 4, sl.e0, sl.e1, 0, 0, it, warp, lane);
+        consume_sub<CPL, FULL, 4>(p, sm, 4 * E, sl.e0, sl.e1, 0, 0, rp, warp, lane);
         consumer_sync();
         if (mine) {
-            const float kv = (float)(sm.scal[0] * (double)sm.res64[ctid] + sm.scal[3]);
+            const long long tot = (sm.res64[4 * ctid] + sm.res64[4 * ctid + 1]) + (sm.res64[4 * ctid + 2] + sm.res64[4 * ctid + 3]);
+            const float kv = (float)(sm.scal[0] * (double)tot + sm.scal[3]);
             sm.xown[ctid] = sm.xown[ctid] + (double)(kv * sm.srown[ctid]);
         }
-        publish_stats(sm, statp(q), ne, ctid);
+        publish_stats(sm, statp(q), ne, rd, ctid);
         grid_sync(p.gbar, target, ctid);
         ++q;
     }
@@ -499,7 +567,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_token(const __grid_constant__ P
     // ======== LN_out for the own slice, head GEMV (rwkv.cu:585-589) ================================
     {
         double xmean, x2;
-        stats_from_parts(p, statp(q - 1), ctid, sm.scratch, xmean, x2);
+        stats_from_parts(p, statp(q - 1), ctid, rd, xmean, x2);
         double mx[3] = {0, 0, 0}, of[3] = {0, 0, 0};
         if (mine) {
             const double *lwp = p.ln + (size_t)(4 * p.L + 2) * E;
@@ -510,12 +578,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_token(const __grid_constant__ P
             of[0] = (double)f * (double)p.ochead[j];
             p.x[j] = sm.xown[ctid]; // residual stream after the last layer (debug / tests)
         }
-        publish_vparts(sm, vpartp(q), 1, mx, of, ctid);
+        publish_vparts<1>(vpartp(q), mx, of, rd, ctid);
     }
     grid_sync(p.gbar, target, ctid);
     ++q;
-    gather_quantise(p, sm, vecp(q - 1), vpartp(q - 1), 1, E, ctid);
-    consume_sub<CPL>(p, sm, E, 1, sl.v0, sl.v1, 0, 0, it, warp, lane);
+    gather_quantise<1, GROUPS>(sm, vecp(q - 1), vpartp(q - 1), E, rd, ctid);
+    consume_sub<CPL, FULL, 1>(p, sm, E, sl.v0, sl.v1, 0, 0, rp, warp, lane);
     consumer_sync();
     {
         float best = -INFINITY;
