@@ -410,6 +410,13 @@ int do_load(M *m, const char *path, int quiet) {
     p.emb = emb; p.ln = ln; p.mixk = mixk; p.mixv = mixv; p.mixr = mixr; p.fmixk = fmk; p.fmixr = fmr;
     p.decay = decay; p.bonus = bonus;
     p.rk = kr; p.rv = vr; p.rr = rr; p.ro = aor; p.rfk = fkr; p.rfv = fvr; p.rfr = frr; p.rhead = hr;
+    {
+        double *ed = nullptr;
+        if ((rc = dmalloc(m, &ed, (size_t)(L * E)))) return rc;
+        rk::k_exp_table<<<(unsigned)((L * E + 255) / 256), 256, 0, m->stream>>>(decay, ed, (size_t)(L * E));
+        CK(cudaGetLastError());
+        p.expdecay = ed;
+    }
     if ((rc = centre(m, kr, o1, L * E, &p.ock))) return rc;
     if ((rc = centre(m, vr, o2, L * E, &p.ocv))) return rc;
     if ((rc = centre(m, rr, o3, L * E, &p.ocr))) return rc;

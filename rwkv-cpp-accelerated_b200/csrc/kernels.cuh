@@ -65,6 +65,7 @@ struct Params {
     const double *ln;                                  // [4(L+1)][E]
     const double *mixk, *mixv, *mixr, *fmixk, *fmixr;  // [L][E]
     const double *decay, *bonus;                       // [L][E]
+    const double *expdecay;                            // [L][E] exp(decay), tabulated at load
     const float *emb;                                  // [V][E]
     double *sxy, *saa, *sbb, *sdd;                     // [slots][L][E]
     double *x;                                         // [E] residual stream
@@ -263,7 +264,7 @@ struct Smem {
     uint8_t *planes;     // limb planes
     long long *res64;    // [kMaxRowsPerCta] exact integer row totals
     double *scratch;     // [16] reductions
-    double *scal;        // [8]  S[0..2], off[0..2]
+    double *scal;        // [8]  S[0..2], off[0..2], then 3 floats: 1/S
     uint64_t *full;      // [stages]
     uint64_t *empty;     // [stages]
     double *red;         // [2][6][8] alternating reduction scratch (token kernel)
@@ -986,6 +987,11 @@ __global__ void __launch_bounds__(256) k_transpose_xor(const uint8_t *__restrict
             if (r < R) out[(size_t)c * ldout + r0 + r] = (int8_t)(t[tx * 4 + e][cc] ^ 0x80);
         }
     }
+}
+
+__global__ void k_exp_table(const double *__restrict__ in, double *__restrict__ out, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = exp(in[i]);
 }
 
 // oc[j] = 128*r[j] + o[j]

@@ -122,8 +122,8 @@ __device__ __forceinline__ void produce_sub(const Params &p, const Smem &sm, con
 // row, one E-byte segment each, segment totals -> res64[res_off + row*4 + seg] (summed by the
 // epilogue; no atomics).
 template <int CPL, bool FULL, int NSEG>
-__device__ __forceinline__ void consume_sub(const Params &p, const Smem &sm, int N, int r0, int r1, int plane_off,
-                                            int res_off, RingPos &rp, int warp, int lane) {
+__device__ __noinline__ RingPos consume_sub(const Params &p, const Smem &sm, int N, int r0, int r1, int plane_off,
+                                            int res_off, RingPos rp, int warp, int lane) {
     const int seg_len = N / NSEG;
     const int nchunks = seg_len >> 4;
     const int seg = warp % NSEG;
@@ -192,6 +192,7 @@ __device__ __forceinline__ void consume_sub(const Params &p, const Smem &sm, int
         if (lane == 0) mbar_arrive(empty0 + 8 * rp.stage);
         rp.advance((uint32_t)p.stages);
     }
+    return rp;
 }
 
 // Slice ownership of this CTA.
@@ -277,52 +278,88 @@ __device__ __forceinline__ void publish_vparts(double *vpart, double *mx, double
     }
 }
 
-// After a barrier: ONE L2 round trip fetches every CTA's partials and the NVEC activation vectors
-// (length N each, NG float4 groups per thread), then one block reduction, then quantisation from
-// registers into the limb planes (vector v at plane offset v*3*N). Leaves S_v / off_v in sm.scal.
-template <int NVEC, int NG>
-__device__ __forceinline__ void gather_quantise(const Smem &sm, const float *vec, const double *vpart, int N, Red &rd,
-                                                int ctid) {
-    double m[NVEC], s[NVEC];
-    float4 f[NVEC][NG];
-    const int ng = N >> 2;
+// Fast activation quantiser for the token kernel (f32 + integer SIMD-in-word, ~12 instructions per
+// element instead of ~30 with f64): u = round(xs*inv + B) with B = 64*(1 + 128 + 128^2) makes the
+// three base-128 digits of u unsigned; limb = digit - 64, produced per byte as sign-extended
+// (digit ^ 0x40). |xs*inv| <= kQMaxTok keeps u inside 21 bits.
+constexpr int kQMaxTok = 1040000;
+constexpr float kQBias = 1056832.0f;
+__device__ __forceinline__ uint32_t spread7(float xs, float inv) {
+    const uint32_t u = (uint32_t)__float2int_rn(fmaf(xs, inv, kQBias));
+    return (u & 0x7Fu) | ((u & 0x3F80u) << 1) | ((u & 0x1FC000u) << 2); // digits in bytes 0,1,2
+}
+__device__ __forceinline__ uint32_t limb_fix(uint32_t w) {
+    const uint32_t x = w ^ 0x40404040u;
+    return x | ((x & 0x40404040u) << 1);
+}
+__device__ __forceinline__ void quantize4f(const float4 f, float inv, uint8_t *planes, int stride, int j) {
+    const uint32_t t0 = spread7(f.x, inv), t1 = spread7(f.y, inv), t2 = spread7(f.z, inv), t3 = spread7(f.w, inv);
+    const uint32_t lo01 = __byte_perm(t0, t1, 0x5140), lo23 = __byte_perm(t2, t3, 0x5140); // [a.b0,b.b0,a.b1,b.b1]
+    const uint32_t hi01 = __byte_perm(t0, t1, 0x0062), hi23 = __byte_perm(t2, t3, 0x0062); // [a.b2,b.b2,..]
+    const uint32_t w0 = __byte_perm(lo01, lo23, 0x5410);
+    const uint32_t w1 = __byte_perm(lo01, lo23, 0x7632);
+    const uint32_t w2 = __byte_perm(hi01, hi23, 0x5410);
+    *reinterpret_cast<uint32_t *>(planes + j) = limb_fix(w0);
+    *reinterpret_cast<uint32_t *>(planes + stride + j) = limb_fix(w1);
+    *reinterpret_cast<uint32_t *>(planes + 2 * stride + j) = limb_fix(w2);
+}
+
+// After a barrier: fetch every CTA's partials and the `nvec` activation vectors of length N
+// (vector v -> limb planes at offset v*3*N), one block reduction, then quantise. Rolled and
+// software-pipelined (two batches of four 16-byte loads in flight) to stay small in the
+// instruction cache: this code runs once per phase and is fetched from L2 every time.
+__device__ __noinline__ int gather_quantise(const Smem sm, const float *vec, const double *vpart, int nvec, int N,
+                                            int red_par, int ctid) {
+    Red rd{sm.red, red_par};
+    const int ng = N >> 2;                                 // float4 groups per vector
+    const int nb = (ng + 4 * kConsumers - 1) / (4 * kConsumers); // batches of 4 groups per thread per vector
+    const int total = nvec * nb;
+    auto load_batch = [&](int t, float4 (&f)[4]) {
+        const int v = t / nb, b = t - v * nb;
+        const float4 *src = reinterpret_cast<const float4 *>(vec + (size_t)v * N);
 #pragma unroll
-    for (int v = 0; v < NVEC; ++v) {
-        m[v] = 0.0;
-        s[v] = 0.0;
+        for (int k = 0; k < 4; ++k) {
+            const int g = ctid + kConsumers * (4 * b + k);
+            f[k] = g < ng ? __ldcg(src + g) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    auto quant_batch = [&](int t, const float4 (&f)[4]) {
+        const int v = t / nb, b = t - v * nb;
+        const float inv = reinterpret_cast<const float *>(sm.scal + 6)[v];
+        uint8_t *pl = sm.planes + (size_t)v * 3 * N;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int g = ctid + kConsumers * (4 * b + k);
+            if (g < ng) quantize4f(f[k], inv, pl, N, 4 * g);
+        }
+    };
+    float4 fa[4], fb[4];
+    load_batch(0, fa); // in flight during the reduction below
+    double m[3] = {0.0, 0.0, 0.0}, s[3] = {0.0, 0.0, 0.0};
+    for (int v = 0; v < nvec; ++v)
         for (int i = ctid; i < (int)gridDim.x; i += kConsumers) {
             m[v] = fmax(m[v], __ldcg(vpart + (v * 2 + 0) * kMaxGrid + i));
             s[v] += __ldcg(vpart + (v * 2 + 1) * kMaxGrid + i);
         }
+    cons_multi<3, 3>(s, m, rd, ctid);
+    if (ctid < 3) {
+        const double mm = ctid == 0 ? m[0] : ctid == 1 ? m[1] : m[2];
+        const double ss = ctid == 0 ? s[0] : ctid == 1 ? s[1] : s[2];
+        sm.scal[ctid] = mm / (double)kQMaxTok;
+        sm.scal[3 + ctid] = ss;
+        reinterpret_cast<float *>(sm.scal + 6)[ctid] = mm > 0.0 ? (float)((double)kQMaxTok / mm) : 0.0f;
     }
-#pragma unroll
-    for (int v = 0; v < NVEC; ++v) {
-        const float4 *src = reinterpret_cast<const float4 *>(vec + (size_t)v * N);
-#pragma unroll
-        for (int g = 0; g < NG; ++g) {
-            const int idx = ctid + kConsumers * g;
-            f[v][g] = idx < ng ? __ldcg(src + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-    }
-    cons_multi<NVEC, NVEC>(s, m, rd, ctid);
-#pragma unroll
-    for (int v = 0; v < NVEC; ++v) {
-        const double inv = m[v] > 0.0 ? (double)kQMax / m[v] : 0.0;
-        if (ctid == 0) {
-            sm.scal[v] = m[v] / (double)kQMax;
-            sm.scal[3 + v] = s[v];
-        }
-        uint8_t *pl = sm.planes + (size_t)v * 3 * N;
-#pragma unroll
-        for (int g = 0; g < NG; ++g) {
-            const int idx = ctid + kConsumers * g;
-            if (idx < ng) {
-                const double xs[4] = {(double)f[v][g].x, (double)f[v][g].y, (double)f[v][g].z, (double)f[v][g].w};
-                quantize4(xs, inv, pl, N, 4 * idx);
-            }
+    consumer_sync();
+    for (int t = 0; t < total; t += 2) {
+        if (t + 1 < total) load_batch(t + 1, fb);
+        quant_batch(t, fa);
+        if (t + 1 < total) {
+            if (t + 2 < total) load_batch(t + 2, fa);
+            quant_batch(t + 1, fb);
         }
     }
     consumer_sync();
+    return rd.par;
 }
 
 // Thread layout of the token kernel: two consumer warpgroups (warps 0-7) + one producer warpgroup
@@ -349,7 +386,6 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
         return;
     }
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kConsumerRegs));
-    constexpr int GROUPS = (CPL + 1) / 2; // float4 groups per thread for a vector of length E
     const int ctid = threadIdx.x;
     const int ne = sl.ne, nk = sl.nk;
     Red rd{sm.red, 0};
@@ -405,7 +441,7 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
             stats_from_parts(p, statp(q - 1), ctid, rd, xmean, x2);
             double mx[3] = {0, 0, 0}, of[3] = {0, 0, 0};
             if (mine) {
-                const double ln = lw * ((sm.xown[ctid] - xmean) / x2) + lb;
+                const double ln = lw * ((sm.xown[ctid] - xmean) * (1.0 / x2)) + lb;
                 const float fk = (float)(mk * ln + (1.0 - mk) * st);
                 const float fv = (float)(mv * ln + (1.0 - mv) * st);
                 const float fr = (float)(mr * ln + (1.0 - mr) * st);
@@ -425,23 +461,24 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
         grid_sync(p.gbar, target, ctid);
         ++q;
         // ======== K, V, R GEMVs for the own channels + WKV (rwkv.cu:542-545) =====================
-        gather_quantise<3, GROUPS>(sm, vecp(q - 1), vpartp(q - 1), E, rd, ctid);
+        rd.par = gather_quantise(sm, vecp(q - 1), vpartp(q - 1), 3, E, rd.par, ctid);
         {
-            double aa = 0, bb = 0, wd = 0, ub = 0;
+            double aa = 0, bb = 0, wd = 0, ub = 0, ewd = 0;
             float ro = 0, oco = 0;
             if (mine) {
                 aa = p.saa[so + lo + j];
                 bb = p.sbb[so + lo + j];
                 wd = p.decay[lo + j];
                 ub = p.bonus[lo + j];
+                ewd = p.expdecay[lo + j];
                 ro = p.ro[lo + j];
                 oco = p.oco[lo + j];
             }
             const size_t mo = (size_t)l * E * E;
             (void)mo;
-            consume_sub<CPL, FULL, 1>(p, sm, E, sl.e0, sl.e1, 0, 0, rp, warp, lane);
-            consume_sub<CPL, FULL, 1>(p, sm, E, sl.e0, sl.e1, 3 * E, ne, rp, warp, lane);
-            consume_sub<CPL, FULL, 1>(p, sm, E, sl.e0, sl.e1, 6 * E, 2 * ne, rp, warp, lane);
+            rp = consume_sub<CPL, FULL, 1>(p, sm, E, sl.e0, sl.e1, 0, 0, rp, warp, lane);
+            rp = consume_sub<CPL, FULL, 1>(p, sm, E, sl.e0, sl.e1, 3 * E, ne, rp, warp, lane);
+            rp = consume_sub<CPL, FULL, 1>(p, sm, E, sl.e0, sl.e1, 6 * E, 2 * ne, rp, warp, lane);
             consumer_sync();
             double mx[3] = {0, 0, 0}, of[3] = {0, 0, 0};
             if (mine) {
@@ -452,7 +489,7 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
                 const double e1 = exp(ub + wd + (double)kf);
                 double y = (aa + e1 * vv) / (bb + e1);
                 y = (1.0 / (1.0 + (double)expf(-rf))) * y;
-                const double ek = exp((double)kf), ew = exp(wd);
+                const double ek = exp((double)kf), ew = ewd; // exp(decay) is static: tabulated at load
                 p.saa[so + lo + j] = (aa + ek * vv) * ew;
                 p.sbb[so + lo + j] = (bb + ek) * ew;
                 const float rw = (float)y;
@@ -466,7 +503,7 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
         grid_sync(p.gbar, target, ctid);
         ++q;
         // ======== out-projection + residual (rwkv.cu:548-553) =====================================
-        gather_quantise<1, GROUPS>(sm, vecp(q - 1), vpartp(q - 1), E, rd, ctid);
+        rd.par = gather_quantise(sm, vecp(q - 1), vpartp(q - 1), 1, E, rd.par, ctid);
         // parameters of the LN2 / ffn token-shift slice computation (used two barriers later)
         double flw = 0, flb = 0, fmk = 0, fmr = 0, fst = 0;
         float frr = 0, frk = 0, forr = 0, fok = 0;
@@ -478,7 +515,7 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
             forr = p.ocfr[lo + j]; fok = p.ocfk[lo + j];
             fst = p.sdd[so + lo + j];
         }
-        consume_sub<CPL, FULL, 1>(p, sm, E, sl.e0, sl.e1, 0, 0, rp, warp, lane);
+        rp = consume_sub<CPL, FULL, 1>(p, sm, E, sl.e0, sl.e1, 0, 0, rp, warp, lane);
         consumer_sync();
         if (mine) {
             const float y = (float)(sm.scal[0] * (double)sm.res64[ctid] + sm.scal[3]);
@@ -494,7 +531,7 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
             stats_from_parts(p, statp(q - 1), ctid, rd, xmean, x2);
             double mx[3] = {0, 0, 0}, of[3] = {0, 0, 0};
             if (mine) {
-                const double ln = flw * ((sm.xown[ctid] - xmean) / x2) + flb;
+                const double ln = flw * ((sm.xown[ctid] - xmean) * (1.0 / x2)) + flb;
                 const float fr = (float)(fmr * ln + (1.0 - fmr) * fst);
                 const float fk = (float)(fmk * ln + (1.0 - fmk) * fst);
                 const float xr = (float)((double)fr * (double)frr);
@@ -511,7 +548,7 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
         grid_sync(p.gbar, target, ctid);
         ++q;
         // ======== ffn R (own slice rows) and ffn K (4E rows) + sigmoid / relu^2 (rwkv.cu:566-573) ==
-        gather_quantise<2, GROUPS>(sm, vecp(q - 1), vpartp(q - 1), E, rd, ctid);
+        rd.par = gather_quantise(sm, vecp(q - 1), vpartp(q - 1), 2, E, rd.par, ctid);
         {
             float rvk[2] = {0, 0}, ovk[2] = {0, 0}; // ffn-V scale / offset of the own K rows (<= 2 per thread)
             const float *rvp = p.rfv + (size_t)l * 4 * E, *ovp = p.ocfv + (size_t)l * 4 * E;
@@ -523,8 +560,8 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
                     ovk[t] = ovp[sl.k0 + i];
                 }
             }
-            consume_sub<CPL, FULL, 1>(p, sm, E, sl.e0, sl.e1, 0, 0, rp, warp, lane);
-            consume_sub<CPL, FULL, 1>(p, sm, E, sl.k0, sl.k1, 3 * E, ne, rp, warp, lane);
+            rp = consume_sub<CPL, FULL, 1>(p, sm, E, sl.e0, sl.e1, 0, 0, rp, warp, lane);
+            rp = consume_sub<CPL, FULL, 1>(p, sm, E, sl.k0, sl.k1, 3 * E, ne, rp, warp, lane);
             consumer_sync();
             if (mine) {
                 const float y = (float)(sm.scal[0] * (double)sm.res64[ctid] + sm.scal[3]);
@@ -550,9 +587,9 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
         grid_sync(p.gbar, target, ctid);
         ++q;
         // ======== ffn V (rows of 4E bytes, four warps per row) + residual (rwkv.cu:574-577) =========
-        gather_quantise<1, 4 * GROUPS>(sm, vecp(q - 1), vpartp(q - 1), 4 * E, rd, ctid);
+        rd.par = gather_quantise(sm, vecp(q - 1), vpartp(q - 1), 1, 4 * E, rd.par, ctid);
         if (l + 1 < p.L_run) prefetch_att(l + 1);
-        consume_sub<CPL, FULL, 4>(p, sm, 4 * E, sl.e0, sl.e1, 0, 0, rp, warp, lane);
+        rp = consume_sub<CPL, FULL, 4>(p, sm, 4 * E, sl.e0, sl.e1, 0, 0, rp, warp, lane);
         consumer_sync();
         if (mine) {
             const long long tot = (sm.res64[4 * ctid] + sm.res64[4 * ctid + 1]) + (sm.res64[4 * ctid + 2] + sm.res64[4 * ctid + 3]);
@@ -571,7 +608,7 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
         double mx[3] = {0, 0, 0}, of[3] = {0, 0, 0};
         if (mine) {
             const double *lwp = p.ln + (size_t)(4 * p.L + 2) * E;
-            const float f = (float)(lwp[j] * ((sm.xown[ctid] - xmean) / x2) + lwp[E + j]);
+            const float f = (float)(lwp[j] * ((sm.xown[ctid] - xmean) * (1.0 / x2)) + lwp[E + j]);
             const float xh = (float)((double)f * (double)p.rhead[j]);
             vecp(q)[j] = xh;
             mx[0] = fabs((double)xh);
@@ -582,8 +619,8 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
     }
     grid_sync(p.gbar, target, ctid);
     ++q;
-    gather_quantise<1, GROUPS>(sm, vecp(q - 1), vpartp(q - 1), E, rd, ctid);
-    consume_sub<CPL, FULL, 1>(p, sm, E, sl.v0, sl.v1, 0, 0, rp, warp, lane);
+    rd.par = gather_quantise(sm, vecp(q - 1), vpartp(q - 1), 1, E, rd.par, ctid);
+    rp = consume_sub<CPL, FULL, 1>(p, sm, E, sl.v0, sl.v1, 0, 0, rp, warp, lane);
     consumer_sync();
     {
         float best = -INFINITY;
