@@ -62,6 +62,7 @@ struct rwkv_b200_model {
     int sms = 0;
     int grid = 0;
     int cpl = 0;
+    int cpl_tok = 0;
     unsigned long long L = 0, E = 0, max_gpt = 1;
     cudaStream_t stream = nullptr;
     rk::Params p{};
@@ -108,6 +109,9 @@ template <int CPL> int set_attrs(size_t smem) {
     CK(cudaFuncSetAttribute(rk::k_ffn_rk<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute(rk::k_ffn_v<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute(rk::k_head<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    return 0;
+}
+template <int CPL> int set_attrs_tok(size_t smem) {
     CK(cudaFuncSetAttribute(rk::k_token<CPL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute(rk::k_token<CPL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     return 0;
@@ -173,18 +177,25 @@ template <int CPL> int launch_token_t(M *m, int feed, bool greedy, const unsigne
     prm.greedy = greedy ? 1 : 0;
     prm.stream = stream;
     void *args[] = {&prm};
-    const void *fn = (m->E == (unsigned long long)CPL * 512) ? (const void *)rk::k_token<CPL, true> : (const void *)rk::k_token<CPL, false>;
+    const void *fn = (m->E == (unsigned long long)CPL * 512 * rk::kRowSplit) ? (const void *)rk::k_token<CPL, true> : (const void *)rk::k_token<CPL, false>;
     CK(cudaLaunchCooperativeKernel(fn, dim3(m->grid), dim3(rk::kTokThreads), args, m->smem, s));
     return 0;
 }
 
 int launch_token(M *m, int feed, bool greedy, const unsigned long long *stream, cudaStream_t s) {
-    switch (m->cpl) {
+    switch (m->cpl_tok) { // 16-byte chunks per lane of one row segment (n_embed / kRowSplit bytes)
+#if RK_TOK_WARPS == 16
+    case 1: return launch_token_t<1>(m, feed, greedy, stream, s);
+    case 2: return launch_token_t<2>(m, feed, greedy, stream, s);
+    case 4: return launch_token_t<4>(m, feed, greedy, stream, s);
+    case 5: return launch_token_t<5>(m, feed, greedy, stream, s);
+#else
     case 2: return launch_token_t<2>(m, feed, greedy, stream, s);
     case 4: return launch_token_t<4>(m, feed, greedy, stream, s);
     case 8: return launch_token_t<8>(m, feed, greedy, stream, s);
     case 10: return launch_token_t<10>(m, feed, greedy, stream, s);
-    default: return fail(3, "unsupported chunks-per-lane %d", m->cpl);
+#endif
+    default: return fail(3, "unsupported chunks-per-lane %d", m->cpl_tok);
     }
 }
 
@@ -360,6 +371,13 @@ int do_load(M *m, const char *path, int quiet) {
     CK(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
 
     m->cpl = E <= 1024 ? 2 : E <= 2048 ? 4 : E <= 4096 ? 8 : 10;
+    {
+        const unsigned long long seg = E / rk::kRowSplit;
+        m->cpl_tok = seg <= 512 ? 1 : seg <= 1024 ? 2 : seg <= 2048 ? 4 : seg <= 2560 ? 5 : seg <= 4096 ? 8 : 10;
+        if (rk::kRowSplit == 1 && m->cpl_tok == 1) m->cpl_tok = 2;
+        if (rk::kRowSplit == 1 && m->cpl_tok == 5) m->cpl_tok = 8;
+        if (E % (16 * rk::kRowSplit) != 0) m->token_mode = false; // segments must be whole 16-byte chunks
+    }
     rk::Params &p = m->p;
     p.L = (int)L;
     p.E = (int)E;
@@ -373,13 +391,27 @@ int do_load(M *m, const char *path, int quiet) {
         (E + m->grid - 1) / m->grid + 1 > (unsigned long long)rk::kMaxSlice ||
         (4 * E + m->grid - 1) / m->grid + 1 > 2ull * rk::kConsumers ||
         (binfmt::kVocab + m->grid - 1) / m->grid + 1 > (unsigned long long)rk::kMaxRowsPerCta ||
-        m->grid > rk::kMaxGrid)
+        m->grid > rk::kRedMax || (4 * E + m->grid - 1) / m->grid + 1 > (unsigned long long)rk::kRedMax)
         return fail(5, "grid of %d CTAs is too small for n_embed=%llu", m->grid, E);
     switch (m->cpl) {
     case 2: rc = set_attrs<2>(m->smem); break;
     case 4: rc = set_attrs<4>(m->smem); break;
     case 8: rc = set_attrs<8>(m->smem); break;
     default: rc = set_attrs<10>(m->smem); break;
+    }
+    if (rc) return rc;
+    switch (m->cpl_tok) {
+#if RK_TOK_WARPS == 16
+    case 1: rc = set_attrs_tok<1>(m->smem); break;
+    case 2: rc = set_attrs_tok<2>(m->smem); break;
+    case 4: rc = set_attrs_tok<4>(m->smem); break;
+    default: rc = set_attrs_tok<5>(m->smem); break;
+#else
+    case 2: rc = set_attrs_tok<2>(m->smem); break;
+    case 4: rc = set_attrs_tok<4>(m->smem); break;
+    case 8: rc = set_attrs_tok<8>(m->smem); break;
+    default: rc = set_attrs_tok<10>(m->smem); break;
+#endif
     }
     if (rc) return rc;
 
@@ -793,7 +825,21 @@ int rwkv_b200_set_option(rwkv_b200_model *m, const char *key, const char *value)
     const std::string k = key;
     const int v = atoi(value);
     if (k == "graph") m->use_graph = v != 0;
-    else if (k == "mode") {
+    else if (k == "trace") {
+        if (v && !m->p.trace) {
+            unsigned long long *t = nullptr;
+            if (dmalloc(m, &t, (size_t)rk::kMaxGrid * rk::kTraceMax)) return fail(1, "trace alloc failed");
+            cudaMemset(t, 0, (size_t)rk::kMaxGrid * rk::kTraceMax * 8);
+            m->p.trace = t;
+            unsigned long long *pt = nullptr;
+            if (dmalloc(m, &pt, (size_t)2 * rk::kRedMax * rk::kTileTraceMax)) return fail(1, "trace alloc failed");
+            cudaMemset(pt, 0, (size_t)2 * rk::kRedMax * rk::kTileTraceMax * 8);
+            m->p.ptrace = pt;
+        } else if (!v) {
+            m->p.trace = nullptr;
+            m->p.ptrace = nullptr;
+        }
+    } else if (k == "mode") {
         if (std::string(value) == "token") m->token_mode = true;
         else if (std::string(value) == "staged") m->token_mode = false;
         else return fail(1, "mode must be 'token' or 'staged'");
@@ -837,6 +883,8 @@ long long rwkv_b200_debug_read(rwkv_b200_model *m, const char *name, void *dst, 
     else if (k == "sr") src = m->p.sr, count = E, bytes = E * 4;
     else if (k == "xs_v") src = m->p.xs_v, count = 4 * E, bytes = 16 * E;
     else if (k == "logits") src = m->p.logits, count = binfmt::kVocab, bytes = 4 * binfmt::kVocab;
+    else if (k == "trace" && m->p.trace) src = m->p.trace, count = (size_t)m->grid * rk::kTraceMax, bytes = count * 8;
+    else if (k == "ptrace" && m->p.ptrace) src = m->p.ptrace, count = (size_t)2 * m->grid * rk::kTileTraceMax, bytes = count * 8;
     else return -1;
     if (dst_bytes < bytes) return -1;
     if (cudaStreamSynchronize(m->stream) != cudaSuccess) return -1;

@@ -37,8 +37,11 @@ constexpr int kConsumerWarps = 8;
 constexpr int kConsumers = kConsumerWarps * 32; // 256
 constexpr int kThreads = kConsumers + 32;       // + producer warp
 constexpr int kMaxStages = 12;
+constexpr int kTileTraceMax = 4096;  // tiles per CTA recorded by the tile trace (debug)
+constexpr int kTraceMax = 2048;      // trace stamps per CTA (token kernel, debug)
+constexpr int kRedMax = 160;         // max contributors to a block reduction (grid size, rows of one CTA)
 constexpr int kMaxSlice = 64;        // max elements of the residual stream one CTA owns (token kernel)
-constexpr int kMaxRowsPerCta = 512; // res64 capacity
+constexpr int kMaxRowsPerCta = 1024; // res64 capacity (rows x segments of one CTA)
 constexpr int kMaxGrid = 1024;      // partials capacity
 constexpr int kQMax = (1 << 20) - 1;
 
@@ -88,6 +91,8 @@ struct Params {
     double *vpart;                     // [2 parity][3][2][kMaxGrid] per-vector partial max|xs|, sum x*oc per CTA
     float *amax_val;                   // [kMaxGrid] per-CTA best logit
     int *amax_idx;                     // [kMaxGrid] and its index
+    unsigned long long *trace;         // optional [grid][kTraceMax] globaltimer stamps (debug), or nullptr
+    unsigned long long *ptrace;        // optional [2][grid][kTileTraceMax]: tile issue / tile ready times (debug)
 };
 
 // ---------------------------------------------------------------------------------------
@@ -264,10 +269,10 @@ struct Smem {
     uint8_t *planes;     // limb planes
     long long *res64;    // [kMaxRowsPerCta] exact integer row totals
     double *scratch;     // [16] reductions
-    double *scal;        // [8]  S[0..2], off[0..2], then 3 floats: 1/S
+    double *scal;        // [12] S[0..2], off[0..2], [6..7] three floats 1/S, [8] trace counter
     uint64_t *full;      // [stages]
     uint64_t *empty;     // [stages]
-    double *red;         // [2][6][8] alternating reduction scratch (token kernel)
+    double *red;         // [6][kRedMax] + [8] block-reduction scratch (token kernel)
     double *xown;        // [kMaxSlice] this CTA's slice of the residual stream (token kernel)
     float *srown;        // [kMaxSlice] sigmoid(ffn r) of the slice
 };
@@ -283,13 +288,13 @@ __device__ __forceinline__ Smem carve(uint8_t *base, const Params &p) {
     s.scratch = reinterpret_cast<double *>(q);
     q += 16 * sizeof(double);
     s.scal = reinterpret_cast<double *>(q);
-    q += 8 * sizeof(double);
+    q += 12 * sizeof(double);
     s.full = reinterpret_cast<uint64_t *>(q);
     q += kMaxStages * sizeof(uint64_t);
     s.empty = reinterpret_cast<uint64_t *>(q);
     q += kMaxStages * sizeof(uint64_t);
     s.red = reinterpret_cast<double *>(q);
-    q += 96 * sizeof(double);
+    q += (6 * kRedMax + 8) * sizeof(double);
     s.xown = reinterpret_cast<double *>(q);
     q += kMaxSlice * sizeof(double);
     s.srown = reinterpret_cast<float *>(q);
@@ -297,8 +302,8 @@ __device__ __forceinline__ Smem carve(uint8_t *base, const Params &p) {
 }
 
 __host__ __device__ inline size_t smem_bytes(int stages, int tile_bytes, int plane_cap) {
-    return (size_t)stages * tile_bytes + plane_cap + kMaxRowsPerCta * 8 + 16 * 8 + 8 * 8 + 2 * kMaxStages * 8 +
-           96 * 8 + kMaxSlice * 12 + 128;
+    return (size_t)stages * tile_bytes + plane_cap + kMaxRowsPerCta * 8 + 16 * 8 + 12 * 8 + 2 * kMaxStages * 8 +
+           (6 * kRedMax + 8) * 8 + kMaxSlice * 12 + 128;
 }
 
 // One streamed sub-matrix of a phase: rows [r0, r1) of a row-major int8 matrix with N bytes

@@ -25,6 +25,38 @@
 
 namespace rk {
 
+// ---- thread layout of the token kernel -------------------------------------------------------
+// Four consumer warpgroups (16 warps) + one producer warpgroup (warp 16 streams weights; its
+// other three warps only donate registers). Every weight row is cut into kRowSplit segments
+// handled by different warps, so a lane holds the limbs of only E/2 inputs: registers per thread
+// halve versus one-warp-per-row, which is what makes four warps per scheduler possible; that
+// occupancy is needed to hide LDS / IDP / REDUX latency in the GEMV core and to run the
+// phase-boundary code at a reasonable IPC. setmaxnreg moves the producer warpgroup's registers
+// to the consumers (40 vs 104; the compile-time budget of a 640-thread CTA is 96).
+#ifndef RK_TOK_WARPS
+#define RK_TOK_WARPS 8
+#endif
+constexpr int kTokWarps = RK_TOK_WARPS;       // 8: one warp per row, 232 regs; 16: two warps per row, 104 regs
+constexpr int kTokConsumers = kTokWarps * 32;
+constexpr int kTokThreads = kTokConsumers + 128;
+constexpr int kProducerRegs = 40;
+// setmaxnreg budget: the consumers may only take what the producer warpgroup gives back
+// (16 warps: compile budget 96, 4 WG x 128 x (104-96) = 4096 <= 128 x (96-40); 8 warps: 168 -> 232).
+constexpr int kConsumerRegs = kTokWarps == 8 ? 232 : 104;
+constexpr int kRowSplit = kTokWarps / 8;      // segments per E-byte row (4E-byte rows: 4 * kRowSplit)
+constexpr int kTokMaxRows = 1024;             // res64 capacity: (rows of one CTA) * segments
+
+__device__ __forceinline__ void tok_sync() { // named barrier 1: the 16 consumer warps
+    asm volatile("bar.sync 1, %0;" ::"n"(kTokConsumers) : "memory");
+}
+
+// weights (signed bytes) x activation digits (unsigned bytes)
+__device__ __forceinline__ int dp4a_su(uint32_t a, uint32_t b, int c) {
+    int d;
+    asm("dp4a.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p) {
     unsigned int v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -33,7 +65,7 @@ __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p) {
 
 // Grid barrier over the consumer threads of all CTAs (the producer warps do not take part).
 __device__ __forceinline__ void grid_sync(unsigned int *bar, unsigned int &target, int ctid) {
-    consumer_sync();
+    tok_sync();
     target += gridDim.x;
     if (ctid == 0) {
         // release: everything this CTA wrote (ordered before by the bar.sync above) is visible to any
@@ -44,47 +76,49 @@ __device__ __forceinline__ void grid_sync(unsigned int *bar, unsigned int &targe
             if (++spins > (1u << 25)) __trap();
         }
     }
-    consumer_sync();
+    tok_sync();
 }
 
-// Multi-value block reductions over the 256 consumer threads with ONE named-barrier each: the
-// scratch area alternates between two buffers, so a reduction never overwrites values that
-// slower threads of the previous reduction may still be reading.
+// Reductions in the phase-boundary code. Only a few threads ever hold data there (the <= 64 slice
+// owners, the <= 160 row owners, or one lane per CTA partial), and warp shuffles are scarce (one
+// warp-wide SHFL per clock per SM), so nothing here involves all eight warps:
+//   owners_reduce : sum / max over the first `nact` threads; warps without data return at once;
+//                   the participating warps shuffle-reduce and meet at named barrier 2.
+//                   The result is valid in thread 0 only (which publishes it).
+// Deterministic (fixed trees). NS sums then NM maxes (maxes are of non-negative values).
 struct Red {
-    double *buf;
+    double *buf; // [2][6][8] alternating scratch
     int par;
 };
 template <int NS, int NM>
-__device__ __forceinline__ void cons_multi(double *s, double *m, Red &rd, int ctid) {
+__device__ __forceinline__ void owners_reduce(double *s, double *m, Red &rd, int ctid, int nact) {
     static_assert(NS + NM <= 6, "reduction scratch holds six values");
+    const int nw = (nact + 31) >> 5;
     const int w = ctid >> 5;
     double *b = rd.buf + rd.par * 48;
+    rd.par ^= 1; // every thread toggles on every call, whether or not its warp takes part
+    if (w >= nw) return;
 #pragma unroll
-    for (int k = 0; k < NS; ++k) {
-        s[k] = warp_sum(s[k]);
-        if ((ctid & 31) == 0) b[k * 8 + w] = s[k];
+    for (int k = 0; k < NS; ++k) s[k] = warp_sum(s[k]);
+#pragma unroll
+    for (int k = 0; k < NM; ++k) m[k] = warp_max(m[k]);
+    if (nw > 1) {
+        if ((ctid & 31) == 0) {
+#pragma unroll
+            for (int k = 0; k < NS; ++k) b[k * 8 + w] = s[k];
+#pragma unroll
+            for (int k = 0; k < NM; ++k) b[(NS + k) * 8 + w] = m[k];
+        }
+        asm volatile("bar.sync 2, %0;" ::"r"(nw * 32) : "memory");
+        if (ctid == 0) {
+            for (int i = 1; i < nw; ++i) {
+#pragma unroll
+                for (int k = 0; k < NS; ++k) s[k] += b[k * 8 + i];
+#pragma unroll
+                for (int k = 0; k < NM; ++k) m[k] = fmax(m[k], b[(NS + k) * 8 + i]);
+            }
+        }
     }
-#pragma unroll
-    for (int k = 0; k < NM; ++k) {
-        m[k] = warp_max(m[k]);
-        if ((ctid & 31) == 0) b[(NS + k) * 8 + w] = m[k];
-    }
-    consumer_sync();
-#pragma unroll
-    for (int k = 0; k < NS; ++k) {
-        double t = 0.0;
-#pragma unroll
-        for (int i = 0; i < kConsumerWarps; ++i) t += b[k * 8 + i];
-        s[k] = t;
-    }
-#pragma unroll
-    for (int k = 0; k < NM; ++k) {
-        double t = b[(NS + k) * 8];
-#pragma unroll
-        for (int i = 1; i < kConsumerWarps; ++i) t = fmax(t, b[(NS + k) * 8 + i]);
-        m[k] = t;
-    }
-    rd.par ^= 1;
 }
 
 // Position in the shared-memory ring: stage index + parity of the current pass over the ring.
@@ -99,7 +133,7 @@ struct RingPos {
 };
 
 __device__ __forceinline__ void produce_sub(const Params &p, const Smem &sm, const int8_t *base, int N, int r0, int r1,
-                                            RingPos &rp, uint64_t policy) {
+                                            RingPos &rp, uint64_t policy, int &tcount) {
     int tr = p.tile_bytes / N;
     if (tr < 1) tr = 1;
     const uint32_t ring = smem_u32(sm.ring);
@@ -112,6 +146,12 @@ __device__ __forceinline__ void produce_sub(const Params &p, const Smem &sm, con
         const uint32_t fb = full0 + 8 * rp.stage;
         mbar_expect_tx(fb, bytes);
         bulk_g2s(ring + rp.stage * (uint32_t)p.tile_bytes, base + (size_t)r * N, bytes, fb, policy);
+        if (p.ptrace != nullptr && tcount < kTileTraceMax) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+            p.ptrace[(size_t)blockIdx.x * kTileTraceMax + tcount] = t;
+        }
+        ++tcount;
         rp.advance((uint32_t)p.stages);
     }
 }
@@ -121,15 +161,27 @@ __device__ __forceinline__ void produce_sub(const Params &p, const Smem &sm, con
 // per row, exact row total -> res64[res_off + row]; NSEG == 4 (rows of 4E bytes): four warps per
 // row, one E-byte segment each, segment totals -> res64[res_off + row*4 + seg] (summed by the
 // epilogue; no atomics).
+// Everything the GEMV core needs, as plain values (shared-space addresses are 32-bit): a noinline
+// function that takes the Smem struct by reference re-reads its fields from LOCAL memory, and with
+// 227 KB of the unified L1/shared array carved out as shared memory every such access is an L2
+// round trip - measured as a ~1300-cycle fixed cost per row.
+struct CoreArgs {
+    uint32_t ring, full0, empty0; // shared addresses
+    uint32_t tile_bytes, stages;
+    unsigned long long *ptrace;   // tile-ready trace (debug) or nullptr
+    int *tile_cnt;                // shared-memory tile counter of the trace
+};
+
 template <int CPL, bool FULL, int NSEG>
-__device__ __noinline__ RingPos consume_sub(const Params &p, const Smem &sm, int N, int r0, int r1, int plane_off,
-                                            int res_off, RingPos rp, int warp, int lane) {
+__device__ __noinline__ RingPos consume_sub(uint32_t ring, uint32_t full0, uint32_t empty0, uint32_t tile_bytes,
+                                            uint32_t stages, uint32_t planes, uint32_t res, int N, int r0, int r1,
+                                            RingPos rp, int warp, int lane, unsigned long long *ptrace, int *tile_cnt) {
     const int seg_len = N / NSEG;
     const int nchunks = seg_len >> 4;
     const int seg = warp % NSEG;
     uint4 a0[CPL], a1[CPL], a2[CPL];
     {
-        const uint32_t pl = smem_u32(sm.planes + plane_off) + (uint32_t)(seg * seg_len);
+        const uint32_t pl = planes + (uint32_t)(seg * seg_len);
 #pragma unroll
         for (int i = 0; i < CPL; ++i) {
             const int c = lane + 32 * i;
@@ -142,18 +194,25 @@ __device__ __noinline__ RingPos consume_sub(const Params &p, const Smem &sm, int
             }
         }
     }
-    int tr = p.tile_bytes / N;
+    int tr = (int)tile_bytes / N;
     if (tr < 1) tr = 1;
-    const uint32_t ring = smem_u32(sm.ring);
-    const uint32_t full0 = smem_u32(sm.full), empty0 = smem_u32(sm.empty);
     const uint32_t lane_off = (uint32_t)(seg * seg_len + lane * 16);
-    int ubase = 0; // units handed out so far in this sub (mod 8); always a multiple of NSEG
+    int ubase = 0; // units handed out so far in this sub (mod kTokWarps); always a multiple of NSEG
     for (int r = r0; r < r1; r += tr) {
         const int rows = min(tr, r1 - r);
         mbar_wait(full0 + 8 * rp.stage, rp.phase);
-        const uint32_t tile = ring + rp.stage * (uint32_t)p.tile_bytes + lane_off;
+        if (ptrace != nullptr && threadIdx.x == 0) {
+            const int c = *tile_cnt;
+            if (c < kTileTraceMax) {
+                unsigned long long t;
+                asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+                ptrace[((size_t)gridDim.x + blockIdx.x) * kTileTraceMax + c] = t;
+            }
+            *tile_cnt = c + 1;
+        }
+        const uint32_t tile = ring + rp.stage * tile_bytes + lane_off;
         const int units = rows * NSEG;
-        for (int u = (warp - ubase) & 7; u < units; u += kConsumerWarps) {
+        for (int u = (warp - ubase) & (kTokWarps - 1); u < units; u += kTokWarps) {
             const int rl = u / NSEG;
             const uint32_t row = tile + (uint32_t)(rl * N);
             // all loads of the row segment first, then the arithmetic: keeps CPL 128-bit LDS in flight
@@ -166,31 +225,35 @@ __device__ __noinline__ RingPos consume_sub(const Params &p, const Smem &sm, int
             int s0a = 0, s0b = 0, s1a = 0, s1b = 0, s2a = 0, s2b = 0;
 #pragma unroll
             for (int i = 0; i < CPL; ++i) {
-                s0a = dp4a_ss(w[i].x, a0[i].x, s0a);
-                s1a = dp4a_ss(w[i].x, a1[i].x, s1a);
+                s0a = dp4a_su(w[i].x, a0[i].x, s0a);
+                s1a = dp4a_su(w[i].x, a1[i].x, s1a);
                 s2a = dp4a_ss(w[i].x, a2[i].x, s2a);
-                s0b = dp4a_ss(w[i].y, a0[i].y, s0b);
-                s1b = dp4a_ss(w[i].y, a1[i].y, s1b);
+                s0b = dp4a_su(w[i].y, a0[i].y, s0b);
+                s1b = dp4a_su(w[i].y, a1[i].y, s1b);
                 s2b = dp4a_ss(w[i].y, a2[i].y, s2b);
-                s0a = dp4a_ss(w[i].z, a0[i].z, s0a);
-                s1a = dp4a_ss(w[i].z, a1[i].z, s1a);
+                s0a = dp4a_su(w[i].z, a0[i].z, s0a);
+                s1a = dp4a_su(w[i].z, a1[i].z, s1a);
                 s2a = dp4a_ss(w[i].z, a2[i].z, s2a);
-                s0b = dp4a_ss(w[i].w, a0[i].w, s0b);
-                s1b = dp4a_ss(w[i].w, a1[i].w, s1b);
+                s0b = dp4a_su(w[i].w, a0[i].w, s0b);
+                s1b = dp4a_su(w[i].w, a1[i].w, s1b);
                 s2b = dp4a_ss(w[i].w, a2[i].w, s2b);
             }
             const int t0 = __reduce_add_sync(0xffffffffu, s0a + s0b);
             const int t1 = __reduce_add_sync(0xffffffffu, s1a + s1b);
             const int t2 = __reduce_add_sync(0xffffffffu, s2a + s2b);
             if (lane == 0) {
-                const long long tot = (((long long)t2 << 7) + (long long)t1) * 128 + (long long)t0;
-                sm.res64[res_off + ((r - r0) + rl) * NSEG + seg] = tot;
+                const long long tot = (((long long)t2 << 8) + (long long)t1) * 256 + (long long)t0;
+                const uint32_t dst = res + (uint32_t)((((r - r0) + rl) * NSEG + seg) * 8);
+                asm volatile("st.shared.u64 [%0], %1;" ::"r"(dst), "l"(tot) : "memory");
             }
         }
-        ubase = (ubase + units) & 7;
+        ubase = (ubase + units) & (kTokWarps - 1);
         __syncwarp();
         if (lane == 0) mbar_arrive(empty0 + 8 * rp.stage);
-        rp.advance((uint32_t)p.stages);
+        if (++rp.stage == stages) {
+            rp.stage = 0;
+            rp.phase ^= 1;
+        }
     }
     return rp;
 }
@@ -217,33 +280,44 @@ __device__ __forceinline__ void produce_token(const Params &p, const Smem &sm, c
     const uint64_t pol = policy_evict_first();
     const int E = p.E;
     RingPos rp{0, 0};
+    int tcount = 0;
     for (int l = 0; l < p.L_run; ++l) {
         const size_t mo = (size_t)l * E * E;
-        produce_sub(p, sm, p.wk + mo, E, sl.e0, sl.e1, rp, pol);
-        produce_sub(p, sm, p.wv + mo, E, sl.e0, sl.e1, rp, pol);
-        produce_sub(p, sm, p.wr + mo, E, sl.e0, sl.e1, rp, pol);
-        produce_sub(p, sm, p.wo + mo, E, sl.e0, sl.e1, rp, pol);
-        produce_sub(p, sm, p.wfr + mo, E, sl.e0, sl.e1, rp, pol);
-        produce_sub(p, sm, p.wfk + 4 * mo, E, sl.k0, sl.k1, rp, pol);
-        produce_sub(p, sm, p.wfv + 4 * mo, 4 * E, sl.e0, sl.e1, rp, pol);
+        produce_sub(p, sm, p.wk + mo, E, sl.e0, sl.e1, rp, pol, tcount);
+        produce_sub(p, sm, p.wv + mo, E, sl.e0, sl.e1, rp, pol, tcount);
+        produce_sub(p, sm, p.wr + mo, E, sl.e0, sl.e1, rp, pol, tcount);
+        produce_sub(p, sm, p.wo + mo, E, sl.e0, sl.e1, rp, pol, tcount);
+        produce_sub(p, sm, p.wfr + mo, E, sl.e0, sl.e1, rp, pol, tcount);
+        produce_sub(p, sm, p.wfk + 4 * mo, E, sl.k0, sl.k1, rp, pol, tcount);
+        produce_sub(p, sm, p.wfv + 4 * mo, 4 * E, sl.e0, sl.e1, rp, pol, tcount);
     }
-    produce_sub(p, sm, p.whead, E, sl.v0, sl.v1, rp, pol);
+    produce_sub(p, sm, p.whead, E, sl.v0, sl.v1, rp, pol, tcount);
 }
 
 // mean / std of the full residual stream from the per-CTA partial sums, with the reference's f32
 // rounding of the two accumulators (rwkv.cu:412-465, 43-44). sum((x-m)^2) = s2 - 2 m s1 + E m^2.
-__device__ __forceinline__ void stats_from_parts(const Params &p, const double *part, int ctid, Red &rd, double &xmean,
-                                                 double &x2) {
-    double s[2] = {0.0, 0.0};
-    for (int i = ctid; i < (int)gridDim.x; i += kConsumers) {
-        s[0] += __ldcg(part + i);
-        s[1] += __ldcg(part + kMaxGrid + i);
+// Warp-local: every warp that calls it loads the partials itself (no block barrier); only the
+// warps that own residual elements call it.
+__device__ __forceinline__ void stats_from_parts(const Params &p, const double *part, int lane, double &xmean, double &x2) {
+    double a1[kRedMax / 32], a2[kRedMax / 32];
+#pragma unroll
+    for (int t = 0; t < kRedMax / 32; ++t) { // all loads in flight: one L2 round trip
+        const int i = lane + 32 * t;
+        a1[t] = i < (int)gridDim.x ? __ldcg(part + i) : 0.0;
+        a2[t] = i < (int)gridDim.x ? __ldcg(part + kMaxGrid + i) : 0.0;
     }
-    cons_multi<2, 0>(s, nullptr, rd, ctid);
+    double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+    for (int t = 0; t < kRedMax / 32; ++t) {
+        s1 += a1[t];
+        s2 += a2[t];
+    }
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
     const double E = (double)p.E;
-    const float mean_acc = (float)s[0];
+    const float mean_acc = (float)s1;
     const double mean_f = (double)(mean_acc / (float)p.E);
-    double var = s[1] - 2.0 * mean_f * s[0] + E * mean_f * mean_f;
+    double var = s2 - 2.0 * mean_f * s1 + E * mean_f * mean_f;
     if (var < 0.0) var = 0.0;
     const float var_acc = (float)var;
     xmean = (double)mean_acc / E;
@@ -258,17 +332,17 @@ __device__ __forceinline__ void publish_stats(const Smem &sm, double *part, int 
         s[0] = v;
         s[1] = v * v;
     }
-    cons_multi<2, 0>(s, nullptr, rd, ctid);
+    owners_reduce<2, 0>(s, nullptr, rd, ctid, ne);
     if (ctid == 0) {
         part[blockIdx.x] = s[0];
         part[kMaxGrid + blockIdx.x] = s[1];
     }
 }
 
-// Publish per-vector partial {max |xs|, sum x*oc} of this CTA.
+// Publish per-vector partial {max |xs|, sum x*oc} of this CTA (data in the first `nact` threads).
 template <int NVEC>
-__device__ __forceinline__ void publish_vparts(double *vpart, double *mx, double *of, Red &rd, int ctid) {
-    cons_multi<NVEC, NVEC>(of, mx, rd, ctid);
+__device__ __forceinline__ void publish_vparts(double *vpart, double *mx, double *of, Red &rd, int ctid, int nact) {
+    owners_reduce<NVEC, NVEC>(of, mx, rd, ctid, nact);
     if (ctid == 0) {
 #pragma unroll
         for (int v = 0; v < NVEC; ++v) {
@@ -278,117 +352,167 @@ __device__ __forceinline__ void publish_vparts(double *vpart, double *mx, double
     }
 }
 
-// Fast activation quantiser for the token kernel (f32 + integer SIMD-in-word, ~12 instructions per
-// element instead of ~30 with f64): u = round(xs*inv + B) with B = 64*(1 + 128 + 128^2) makes the
-// three base-128 digits of u unsigned; limb = digit - 64, produced per byte as sign-extended
-// (digit ^ 0x40). |xs*inv| <= kQMaxTok keeps u inside 21 bits.
-constexpr int kQMaxTok = 1040000;
-constexpr float kQBias = 1056832.0f;
-__device__ __forceinline__ uint32_t spread7(float xs, float inv) {
-    const uint32_t u = (uint32_t)__float2int_rn(fmaf(xs, inv, kQBias));
-    return (u & 0x7Fu) | ((u & 0x3F80u) << 1) | ((u & 0x1FC000u) << 2); // digits in bytes 0,1,2
-}
-__device__ __forceinline__ uint32_t limb_fix(uint32_t w) {
-    const uint32_t x = w ^ 0x40404040u;
-    return x | ((x & 0x40404040u) << 1);
+// Activation quantiser of the token kernel: q = round(xs * inv) as a 23-bit two's complement integer
+// (|q| <= 2^22 - 1), and the three limb planes are simply its three low BYTES: bytes 0 and 1 are
+// unsigned digits, byte 2 is the signed top digit, q = b2*65536 + b1*256 + b0. The GEMV uses
+// dp4a.s32.u32 for the two unsigned planes and dp4a.s32.s32 for the signed one (all exact int32).
+// Rounding goes through the float adder (1.5*2^23 + x has ulp 1; the low mantissa bits are the
+// integer) - no F2I, no per-digit bit surgery; four elements are transposed with seven PRMTs.
+constexpr int kQMaxTok = 4194303; // 2^22 - 1
+__device__ __forceinline__ uint32_t round_q(float xs, float inv) {
+    return __float_as_uint(fmaf(xs, inv, 12582912.0f)) - 0x4B400000u; // two's complement q
 }
 __device__ __forceinline__ void quantize4f(const float4 f, float inv, uint8_t *planes, int stride, int j) {
-    const uint32_t t0 = spread7(f.x, inv), t1 = spread7(f.y, inv), t2 = spread7(f.z, inv), t3 = spread7(f.w, inv);
+    const uint32_t t0 = round_q(f.x, inv), t1 = round_q(f.y, inv), t2 = round_q(f.z, inv), t3 = round_q(f.w, inv);
     const uint32_t lo01 = __byte_perm(t0, t1, 0x5140), lo23 = __byte_perm(t2, t3, 0x5140); // [a.b0,b.b0,a.b1,b.b1]
     const uint32_t hi01 = __byte_perm(t0, t1, 0x0062), hi23 = __byte_perm(t2, t3, 0x0062); // [a.b2,b.b2,..]
-    const uint32_t w0 = __byte_perm(lo01, lo23, 0x5410);
-    const uint32_t w1 = __byte_perm(lo01, lo23, 0x7632);
-    const uint32_t w2 = __byte_perm(hi01, hi23, 0x5410);
-    *reinterpret_cast<uint32_t *>(planes + j) = limb_fix(w0);
-    *reinterpret_cast<uint32_t *>(planes + stride + j) = limb_fix(w1);
-    *reinterpret_cast<uint32_t *>(planes + 2 * stride + j) = limb_fix(w2);
+    *reinterpret_cast<uint32_t *>(planes + j) = __byte_perm(lo01, lo23, 0x5410);
+    *reinterpret_cast<uint32_t *>(planes + stride + j) = __byte_perm(lo01, lo23, 0x7632);
+    *reinterpret_cast<uint32_t *>(planes + 2 * stride + j) = __byte_perm(hi01, hi23, 0x5410);
+}
+
+// Debug tracing: thread 0 of each CTA appends %globaltimer to its row of `trace`.
+__device__ __forceinline__ void trace_stamp(unsigned long long *trace, const Smem &sm, int ctid) {
+    if (trace != nullptr && ctid == 0) {
+        int *cnt = reinterpret_cast<int *>(sm.scal + 8);
+        const int c = *cnt;
+        if (c < kTraceMax) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+            trace[(size_t)blockIdx.x * kTraceMax + c] = t;
+            *cnt = c + 1;
+        }
+    }
+}
+
+__device__ __forceinline__ void trace_stamp2(unsigned long long *trace, double *scal, int ctid) {
+    if (trace != nullptr && ctid == 0) {
+        int *cnt = reinterpret_cast<int *>(scal + 8);
+        const int c = *cnt;
+        if (c < kTraceMax) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+            trace[(size_t)blockIdx.x * kTraceMax + c] = t;
+            *cnt = c + 1;
+        }
+    }
 }
 
 // After a barrier: fetch every CTA's partials and the `nvec` activation vectors of length N
-// (vector v -> limb planes at offset v*3*N), one block reduction, then quantise. Rolled and
-// software-pipelined (two batches of four 16-byte loads in flight) to stay small in the
-// instruction cache: this code runs once per phase and is fetched from L2 every time.
-__device__ __noinline__ int gather_quantise(const Smem sm, const float *vec, const double *vpart, int nvec, int N,
-                                            int red_par, int ctid) {
-    Red rd{sm.red, red_par};
-    const int ng = N >> 2;                                 // float4 groups per vector
-    const int nb = (ng + 4 * kConsumers - 1) / (4 * kConsumers); // batches of 4 groups per thread per vector
-    const int total = nvec * nb;
-    auto load_batch = [&](int t, float4 (&f)[4]) {
-        const int v = t / nb, b = t - v * nb;
-        const float4 *src = reinterpret_cast<const float4 *>(vec + (size_t)v * N);
+// (vector v -> limb planes at offset v*3*N), one block reduction, then quantise from registers.
+// All loads (up to 24 x 16 B per thread) are issued before anything is consumed, so the whole
+// gather costs ONE L2 round trip; every CTA walks the vector from a different starting offset so
+// that the 148 CTAs do not hit the same L2 lines at the same moment.
+constexpr int kGatherBatches = kTokWarps == 8 ? 6 : 3; // x 4 float4 groups x threads x 4 elements >= 4*5120
+__device__ __noinline__ void gather_quantise(uint8_t *planes, double *scal, const float *vec, const double *vpart,
+                                             int nvec, int N, int ctid, unsigned long long *trace) {
+    const int ng = N >> 2;                                       // float4 groups per vector
+    const int nb = (ng + 4 * kTokConsumers - 1) / (4 * kTokConsumers); // batches of 4 groups per thread per vector
+    const int total = nvec * nb;                                 // <= kGatherBatches
+    const int rot = (int)(((long long)ng * blockIdx.x) / gridDim.x);
+    float4 f[kGatherBatches][4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int g = ctid + kConsumers * (4 * b + k);
-            f[k] = g < ng ? __ldcg(src + g) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-    };
-    auto quant_batch = [&](int t, const float4 (&f)[4]) {
-        const int v = t / nb, b = t - v * nb;
-        const float inv = reinterpret_cast<const float *>(sm.scal + 6)[v];
-        uint8_t *pl = sm.planes + (size_t)v * 3 * N;
+    for (int t = 0; t < kGatherBatches; ++t) {
+        if (t < total) {
+            const int v = t / nb, b = t - v * nb;
+            const float4 *src = reinterpret_cast<const float4 *>(vec + (size_t)v * N);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int g = ctid + kConsumers * (4 * b + k);
-            if (g < ng) quantize4f(f[k], inv, pl, N, 4 * g);
-        }
-    };
-    float4 fa[4], fb[4];
-    load_batch(0, fa); // in flight during the reduction below
-    double m[3] = {0.0, 0.0, 0.0}, s[3] = {0.0, 0.0, 0.0};
-    for (int v = 0; v < nvec; ++v)
-        for (int i = ctid; i < (int)gridDim.x; i += kConsumers) {
-            m[v] = fmax(m[v], __ldcg(vpart + (v * 2 + 0) * kMaxGrid + i));
-            s[v] += __ldcg(vpart + (v * 2 + 1) * kMaxGrid + i);
-        }
-    cons_multi<3, 3>(s, m, rd, ctid);
-    if (ctid < 3) {
-        const double mm = ctid == 0 ? m[0] : ctid == 1 ? m[1] : m[2];
-        const double ss = ctid == 0 ? s[0] : ctid == 1 ? s[1] : s[2];
-        sm.scal[ctid] = mm / (double)kQMaxTok;
-        sm.scal[3 + ctid] = ss;
-        reinterpret_cast<float *>(sm.scal + 6)[ctid] = mm > 0.0 ? (float)((double)kQMaxTok / mm) : 0.0f;
-    }
-    consumer_sync();
-    for (int t = 0; t < total; t += 2) {
-        if (t + 1 < total) load_batch(t + 1, fb);
-        quant_batch(t, fa);
-        if (t + 1 < total) {
-            if (t + 2 < total) load_batch(t + 2, fa);
-            quant_batch(t + 1, fb);
+            for (int k = 0; k < 4; ++k) {
+                const int g = ctid + kTokConsumers * (4 * b + k);
+                int gg = g + rot;
+                if (gg >= ng) gg -= ng;
+                f[t][k] = g < ng ? __ldcg(src + gg) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
         }
     }
-    consumer_sync();
-    return rd.par;
+    trace_stamp2(trace, scal, ctid); // loads issued
+    if (ctid < 32) { // warp 0 combines the per-CTA partials (grid <= 160: five records per lane)
+        double pm[3][kRedMax / 32], ps[3][kRedMax / 32];
+#pragma unroll
+        for (int v = 0; v < 3; ++v)
+#pragma unroll
+            for (int t = 0; t < kRedMax / 32; ++t) { // all loads in flight: one L2 round trip
+                const int i = ctid + 32 * t;
+                const bool on = v < nvec && i < (int)gridDim.x;
+                pm[v][t] = on ? __ldcg(vpart + (v * 2 + 0) * kMaxGrid + i) : 0.0;
+                ps[v][t] = on ? __ldcg(vpart + (v * 2 + 1) * kMaxGrid + i) : 0.0;
+            }
+        double m[3] = {0.0, 0.0, 0.0}, s[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+        for (int v = 0; v < 3; ++v) {
+#pragma unroll
+            for (int t = 0; t < kRedMax / 32; ++t) {
+                m[v] = fmax(m[v], pm[v][t]);
+                s[v] += ps[v][t];
+            }
+            m[v] = warp_max(m[v]);
+            s[v] = warp_sum(s[v]);
+        }
+        if (ctid < 3) {
+            const double mm = ctid == 0 ? m[0] : ctid == 1 ? m[1] : m[2];
+            const double ss = ctid == 0 ? s[0] : ctid == 1 ? s[1] : s[2];
+            scal[ctid] = mm / (double)kQMaxTok;
+            scal[3 + ctid] = ss;
+            reinterpret_cast<float *>(scal + 6)[ctid] = mm > 0.0 ? (float)((double)kQMaxTok / mm) : 0.0f;
+        }
+    }
+    tok_sync();
+    trace_stamp2(trace, scal, ctid); // scales known
+    float inv[3];
+#pragma unroll
+    for (int v = 0; v < 3; ++v) inv[v] = reinterpret_cast<const float *>(scal + 6)[v];
+#pragma unroll
+    for (int t = 0; t < kGatherBatches; ++t) {
+        if (t < total) {
+            const int v = t / nb, b = t - v * nb;
+            const float iv = v == 0 ? inv[0] : v == 1 ? inv[1] : inv[2];
+            uint8_t *pl = planes + (size_t)v * 3 * N;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int g = ctid + kTokConsumers * (4 * b + k);
+                int gg = g + rot;
+                if (gg >= ng) gg -= ng;
+                if (g < ng) quantize4f(f[t][k], iv, pl, N, 4 * gg);
+            }
+        }
+    }
+    trace_stamp2(trace, scal, ctid); // own quantisation done
+    tok_sync();
 }
 
-// Thread layout of the token kernel: two consumer warpgroups (warps 0-7) + one producer warpgroup
-// (warp 8 streams weights, warps 9-11 only donate their registers). With 384 threads the compiler
-// budget is 168 registers/thread; `setmaxnreg` then moves the producer warpgroup's share to the
-// consumers (40 vs 232), which is what lets ptxas keep CPL 128-bit LDS in flight next to the
-// CPL*12 limb registers without spilling.
-constexpr int kTokThreads = 384;
-constexpr int kProducerRegs = 40;
-constexpr int kConsumerRegs = 232;
-
-// CPL: 16-byte chunks per lane; FULL: n_embed == CPL*512, i.e. no lane is ever out of range.
+// CPL: 16-byte chunks per lane of one row segment (E / kRowSplit bytes);
+// FULL: E / kRowSplit == CPL*512, i.e. no lane is ever out of range.
 template <int CPL, bool FULL>
 __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant__ Params p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const Smem sm = carve(smem_raw, p);
-    init_barriers(p, sm);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < p.stages; ++i) {
+            mbar_init(smem_u32(&sm.full[i]), 1);
+            mbar_init(smem_u32(&sm.empty[i]), kTokWarps);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
     const int E = p.E;
     const Slices sl = make_slices(E);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (warp >= kConsumerWarps) {
+    if (warp >= kTokWarps) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kProducerRegs));
-        if (warp == kConsumerWarps && lane == 0) produce_token(p, sm, sl);
+        if (warp == kTokWarps && lane == 0) produce_token(p, sm, sl);
         return;
     }
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kConsumerRegs));
     const int ctid = threadIdx.x;
     const int ne = sl.ne, nk = sl.nk;
+    const int nwe = (ne + 31) >> 5; // warps that own residual elements
     Red rd{sm.red, 0};
+    if (ctid == 0) {
+        *reinterpret_cast<int *>(sm.scal + 8) = 0;
+        *reinterpret_cast<int *>(sm.scal + 9) = 0;
+    }
+    auto stamp = [&]() { trace_stamp(p.trace, sm, ctid); };
+    stamp();
     const bool mine = ctid < ne;      // this thread owns residual element j
     const int j = sl.e0 + (mine ? ctid : 0);
     Ctrl *ctrl = p.ctrl;
@@ -399,6 +523,15 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
     const size_t so = (size_t)ctrl->slot * p.L * E; // state slot offset
     unsigned int q = 0;                              // exchange-buffer parity counter (one per barrier)
     RingPos rp{0, 0};
+    const uint32_t c_ring = smem_u32(sm.ring), c_full = smem_u32(sm.full), c_empty = smem_u32(sm.empty);
+    const uint32_t c_planes = smem_u32(sm.planes), c_res = smem_u32(sm.res64);
+    int *const c_tcnt = reinterpret_cast<int *>(sm.scal + 9);
+    // exact integer total of row `i` of a sub whose partials start at `off` (nseg segments per row)
+    auto row_total = [&](int off, int i, int nseg) {
+        long long t = 0;
+        for (int sgm = 0; sgm < nseg; ++sgm) t += sm.res64[off + i * nseg + sgm];
+        return (double)t;
+    };
     auto statp = [&](unsigned int qq) { return p.stat_part + (size_t)(qq & 1) * 2 * kMaxGrid; };
     auto vecp = [&](unsigned int qq) { return p.vec + (size_t)(qq & 1) * 4 * E; };
     auto vpartp = [&](unsigned int qq) { return p.vpart + (size_t)(qq & 1) * 6 * kMaxGrid; };
@@ -410,8 +543,36 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
             const float4 f = *reinterpret_cast<const float4 *>(row + 4 * g);
             v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
         };
-        double xmean, x2;
-        ln_stats(E, ctid, sm.scratch, loadx, xmean, x2);
+        // two-pass statistics of the embedding row with the reference's f32 rounding (rwkv.cu:412-465)
+        double *sc = sm.red; // [32] scratch: 16 warp sums
+        double sacc = 0.0;
+        for (int g = ctid; g < (E >> 2); g += kTokConsumers) {
+            double v[4];
+            loadx(g, v);
+            sacc += (v[0] + v[1]) + (v[2] + v[3]);
+        }
+        sacc = warp_sum(sacc);
+        if (lane == 0) sc[warp] = sacc;
+        tok_sync();
+        double tot = 0.0;
+        for (int w = 0; w < kTokWarps; ++w) tot += sc[w];
+        const float mean_acc = (float)tot;
+        const double mean_f = (double)(mean_acc / (float)E);
+        double qacc = 0.0;
+        for (int g = ctid; g < (E >> 2); g += kTokConsumers) {
+            double v[4];
+            loadx(g, v);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) qacc += (v[e] - mean_f) * (v[e] - mean_f);
+        }
+        qacc = warp_sum(qacc);
+        if (lane == 0) sc[16 + warp] = qacc;
+        tok_sync();
+        double qtot = 0.0;
+        for (int w = 0; w < kTokWarps; ++w) qtot += sc[16 + w];
+        const double xmean = (double)mean_acc / (double)E;
+        const double x2 = (double)sqrtf((float)qtot / (float)(E - 1));
+        tok_sync(); // scratch is reused by owners_reduce below
         if (mine) sm.xown[ctid] = p.ln[j] * (((double)row[j] - xmean) / x2) + p.ln[E + j];
         publish_stats(sm, statp(q), ne, rd, ctid);
     }
@@ -430,15 +591,17 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
         }
     };
     if (p.L_run > 0) prefetch_att(0);
+    stamp();
     grid_sync(p.gbar, target, ctid);
+    stamp();
     ++q;
 
     for (int l = 0; l < p.L_run; ++l) {
         const size_t lo = (size_t)l * E;
         // ======== LN1 + token shift for the own slice (rwkv.cu:535-540) ==========================
         {
-            double xmean, x2;
-            stats_from_parts(p, statp(q - 1), ctid, rd, xmean, x2);
+            double xmean = 0.0, x2 = 1.0;
+            if (warp < nwe) stats_from_parts(p, statp(q - 1), lane, xmean, x2);
             double mx[3] = {0, 0, 0}, of[3] = {0, 0, 0};
             if (mine) {
                 const double ln = lw * ((sm.xown[ctid] - xmean) * (1.0 / x2)) + lb;
@@ -456,12 +619,15 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
                 of[0] = (double)fk * (double)ok; of[1] = (double)fv * (double)ov; of[2] = (double)fr * (double)orr;
                 p.sxy[so + lo + j] = ln; // only the owner ever reads or writes this element
             }
-            publish_vparts<3>(vpartp(q), mx, of, rd, ctid);
+            publish_vparts<3>(vpartp(q), mx, of, rd, ctid, ne);
         }
-        grid_sync(p.gbar, target, ctid);
+        stamp();
+    grid_sync(p.gbar, target, ctid);
+    stamp();
         ++q;
         // ======== K, V, R GEMVs for the own channels + WKV (rwkv.cu:542-545) =====================
-        rd.par = gather_quantise(sm, vecp(q - 1), vpartp(q - 1), 3, E, rd.par, ctid);
+        gather_quantise(sm.planes, sm.scal, vecp(q - 1), vpartp(q - 1), 3, E, ctid, p.trace);
+        stamp();
         {
             double aa = 0, bb = 0, wd = 0, ub = 0, ewd = 0;
             float ro = 0, oco = 0;
@@ -476,15 +642,16 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
             }
             const size_t mo = (size_t)l * E * E;
             (void)mo;
-            rp = consume_sub<CPL, FULL, 1>(p, sm, E, sl.e0, sl.e1, 0, 0, rp, warp, lane);
-            rp = consume_sub<CPL, FULL, 1>(p, sm, E, sl.e0, sl.e1, 3 * E, ne, rp, warp, lane);
-            rp = consume_sub<CPL, FULL, 1>(p, sm, E, sl.e0, sl.e1, 6 * E, 2 * ne, rp, warp, lane);
-            consumer_sync();
+            rp = consume_sub<CPL, FULL, kRowSplit>(c_ring, c_full, c_empty, (uint32_t)p.tile_bytes, (uint32_t)p.stages, c_planes + (uint32_t)(0), c_res + (uint32_t)(0) * 8u, E, sl.e0, sl.e1, rp, warp, lane, p.ptrace, c_tcnt);
+            rp = consume_sub<CPL, FULL, kRowSplit>(c_ring, c_full, c_empty, (uint32_t)p.tile_bytes, (uint32_t)p.stages, c_planes + (uint32_t)(3 * E), c_res + (uint32_t)(ne * kRowSplit) * 8u, E, sl.e0, sl.e1, rp, warp, lane, p.ptrace, c_tcnt);
+            rp = consume_sub<CPL, FULL, kRowSplit>(c_ring, c_full, c_empty, (uint32_t)p.tile_bytes, (uint32_t)p.stages, c_planes + (uint32_t)(6 * E), c_res + (uint32_t)(2 * ne * kRowSplit) * 8u, E, sl.e0, sl.e1, rp, warp, lane, p.ptrace, c_tcnt);
+            tok_sync();
+            stamp();
             double mx[3] = {0, 0, 0}, of[3] = {0, 0, 0};
             if (mine) {
-                const float kf = (float)(sm.scal[0] * (double)sm.res64[ctid] + sm.scal[3]);
-                const float vf = (float)(sm.scal[1] * (double)sm.res64[ne + ctid] + sm.scal[4]);
-                const float rf = (float)(sm.scal[2] * (double)sm.res64[2 * ne + ctid] + sm.scal[5]);
+                const float kf = (float)(sm.scal[0] * row_total(0, ctid, kRowSplit) + sm.scal[3]);
+                const float vf = (float)(sm.scal[1] * row_total(ne * kRowSplit, ctid, kRowSplit) + sm.scal[4]);
+                const float rf = (float)(sm.scal[2] * row_total(2 * ne * kRowSplit, ctid, kRowSplit) + sm.scal[5]);
                 const double vv = (double)vf;
                 const double e1 = exp(ub + wd + (double)kf);
                 double y = (aa + e1 * vv) / (bb + e1);
@@ -498,12 +665,15 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
                 mx[0] = fabs((double)xo);
                 of[0] = (double)rw * (double)oco;
             }
-            publish_vparts<1>(vpartp(q), mx, of, rd, ctid);
+            publish_vparts<1>(vpartp(q), mx, of, rd, ctid, ne);
         }
-        grid_sync(p.gbar, target, ctid);
+        stamp();
+    grid_sync(p.gbar, target, ctid);
+    stamp();
         ++q;
         // ======== out-projection + residual (rwkv.cu:548-553) =====================================
-        rd.par = gather_quantise(sm, vecp(q - 1), vpartp(q - 1), 1, E, rd.par, ctid);
+        gather_quantise(sm.planes, sm.scal, vecp(q - 1), vpartp(q - 1), 1, E, ctid, p.trace);
+        stamp();
         // parameters of the LN2 / ffn token-shift slice computation (used two barriers later)
         double flw = 0, flb = 0, fmk = 0, fmr = 0, fst = 0;
         float frr = 0, frk = 0, forr = 0, fok = 0;
@@ -515,20 +685,23 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
             forr = p.ocfr[lo + j]; fok = p.ocfk[lo + j];
             fst = p.sdd[so + lo + j];
         }
-        rp = consume_sub<CPL, FULL, 1>(p, sm, E, sl.e0, sl.e1, 0, 0, rp, warp, lane);
-        consumer_sync();
+        rp = consume_sub<CPL, FULL, kRowSplit>(c_ring, c_full, c_empty, (uint32_t)p.tile_bytes, (uint32_t)p.stages, c_planes + (uint32_t)(0), c_res + (uint32_t)(0) * 8u, E, sl.e0, sl.e1, rp, warp, lane, p.ptrace, c_tcnt);
+        tok_sync();
+        stamp();
         if (mine) {
-            const float y = (float)(sm.scal[0] * (double)sm.res64[ctid] + sm.scal[3]);
+            const float y = (float)(sm.scal[0] * row_total(0, ctid, kRowSplit) + sm.scal[3]);
             const float xf = (float)sm.xown[ctid] + y;
             sm.xown[ctid] = (double)xf;
         }
         publish_stats(sm, statp(q), ne, rd, ctid);
-        grid_sync(p.gbar, target, ctid);
+        stamp();
+    grid_sync(p.gbar, target, ctid);
+    stamp();
         ++q;
         // ======== LN2 + token shift for the own slice (rwkv.cu:557-562) ===========================
         {
-            double xmean, x2;
-            stats_from_parts(p, statp(q - 1), ctid, rd, xmean, x2);
+            double xmean = 0.0, x2 = 1.0;
+            if (warp < nwe) stats_from_parts(p, statp(q - 1), lane, xmean, x2);
             double mx[3] = {0, 0, 0}, of[3] = {0, 0, 0};
             if (mine) {
                 const double ln = flw * ((sm.xown[ctid] - xmean) * (1.0 / x2)) + flb;
@@ -543,37 +716,41 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
                 of[0] = (double)fr * (double)forr; of[1] = (double)fk * (double)fok;
                 p.sdd[so + lo + j] = ln;
             }
-            publish_vparts<2>(vpartp(q), mx, of, rd, ctid);
+            publish_vparts<2>(vpartp(q), mx, of, rd, ctid, ne);
         }
-        grid_sync(p.gbar, target, ctid);
+        stamp();
+    grid_sync(p.gbar, target, ctid);
+    stamp();
         ++q;
         // ======== ffn R (own slice rows) and ffn K (4E rows) + sigmoid / relu^2 (rwkv.cu:566-573) ==
-        rd.par = gather_quantise(sm, vecp(q - 1), vpartp(q - 1), 2, E, rd.par, ctid);
+        gather_quantise(sm.planes, sm.scal, vecp(q - 1), vpartp(q - 1), 2, E, ctid, p.trace);
+        stamp();
         {
             float rvk[2] = {0, 0}, ovk[2] = {0, 0}; // ffn-V scale / offset of the own K rows (<= 2 per thread)
             const float *rvp = p.rfv + (size_t)l * 4 * E, *ovp = p.ocfv + (size_t)l * 4 * E;
 #pragma unroll
             for (int t = 0; t < 2; ++t) {
-                const int i = ctid + t * kConsumers;
+                const int i = ctid + t * kTokConsumers;
                 if (i < nk) {
                     rvk[t] = rvp[sl.k0 + i];
                     ovk[t] = ovp[sl.k0 + i];
                 }
             }
-            rp = consume_sub<CPL, FULL, 1>(p, sm, E, sl.e0, sl.e1, 0, 0, rp, warp, lane);
-            rp = consume_sub<CPL, FULL, 1>(p, sm, E, sl.k0, sl.k1, 3 * E, ne, rp, warp, lane);
-            consumer_sync();
+            rp = consume_sub<CPL, FULL, kRowSplit>(c_ring, c_full, c_empty, (uint32_t)p.tile_bytes, (uint32_t)p.stages, c_planes + (uint32_t)(0), c_res + (uint32_t)(0) * 8u, E, sl.e0, sl.e1, rp, warp, lane, p.ptrace, c_tcnt);
+            rp = consume_sub<CPL, FULL, kRowSplit>(c_ring, c_full, c_empty, (uint32_t)p.tile_bytes, (uint32_t)p.stages, c_planes + (uint32_t)(3 * E), c_res + (uint32_t)(ne * kRowSplit) * 8u, E, sl.k0, sl.k1, rp, warp, lane, p.ptrace, c_tcnt);
+            tok_sync();
+            stamp();
             if (mine) {
-                const float y = (float)(sm.scal[0] * (double)sm.res64[ctid] + sm.scal[3]);
+                const float y = (float)(sm.scal[0] * row_total(0, ctid, kRowSplit) + sm.scal[3]);
                 sm.srown[ctid] = (float)(1.0 / (1.0 + exp(-(double)y)));
             }
             double mx[3] = {0, 0, 0}, of[3] = {0, 0, 0};
             float *vec = vecp(q);
 #pragma unroll
             for (int t = 0; t < 2; ++t) {
-                const int i = ctid + t * kConsumers;
+                const int i = ctid + t * kTokConsumers;
                 if (i < nk) {
-                    float a = (float)(sm.scal[1] * (double)sm.res64[ne + i] + sm.scal[4]);
+                    float a = (float)(sm.scal[1] * row_total(ne * kRowSplit, i, kRowSplit) + sm.scal[4]);
                     a = a > 0.0f ? a : 0.0f;
                     a = a * a;
                     const float xv = (float)((double)a * (double)rvk[t]);
@@ -582,29 +759,34 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
                     of[0] += (double)a * (double)ovk[t];
                 }
             }
-            publish_vparts<1>(vpartp(q), mx, of, rd, ctid);
+            publish_vparts<1>(vpartp(q), mx, of, rd, ctid, nk < kRedMax ? nk : kRedMax);
         }
-        grid_sync(p.gbar, target, ctid);
+        stamp();
+    grid_sync(p.gbar, target, ctid);
+    stamp();
         ++q;
         // ======== ffn V (rows of 4E bytes, four warps per row) + residual (rwkv.cu:574-577) =========
-        rd.par = gather_quantise(sm, vecp(q - 1), vpartp(q - 1), 1, 4 * E, rd.par, ctid);
+        gather_quantise(sm.planes, sm.scal, vecp(q - 1), vpartp(q - 1), 1, 4 * E, ctid, p.trace);
+        stamp();
         if (l + 1 < p.L_run) prefetch_att(l + 1);
-        rp = consume_sub<CPL, FULL, 4>(p, sm, 4 * E, sl.e0, sl.e1, 0, 0, rp, warp, lane);
-        consumer_sync();
+        rp = consume_sub<CPL, FULL, 4 * kRowSplit>(c_ring, c_full, c_empty, (uint32_t)p.tile_bytes, (uint32_t)p.stages, c_planes + (uint32_t)(0), c_res + (uint32_t)(0) * 8u, 4 * E, sl.e0, sl.e1, rp, warp, lane, p.ptrace, c_tcnt);
+        tok_sync();
+        stamp();
         if (mine) {
-            const long long tot = (sm.res64[4 * ctid] + sm.res64[4 * ctid + 1]) + (sm.res64[4 * ctid + 2] + sm.res64[4 * ctid + 3]);
-            const float kv = (float)(sm.scal[0] * (double)tot + sm.scal[3]);
+            const float kv = (float)(sm.scal[0] * row_total(0, ctid, 4 * kRowSplit) + sm.scal[3]);
             sm.xown[ctid] = sm.xown[ctid] + (double)(kv * sm.srown[ctid]);
         }
         publish_stats(sm, statp(q), ne, rd, ctid);
-        grid_sync(p.gbar, target, ctid);
+        stamp();
+    grid_sync(p.gbar, target, ctid);
+    stamp();
         ++q;
     }
 
     // ======== LN_out for the own slice, head GEMV (rwkv.cu:585-589) ================================
     {
-        double xmean, x2;
-        stats_from_parts(p, statp(q - 1), ctid, rd, xmean, x2);
+        double xmean = 0.0, x2 = 1.0;
+        if (warp < nwe) stats_from_parts(p, statp(q - 1), lane, xmean, x2);
         double mx[3] = {0, 0, 0}, of[3] = {0, 0, 0};
         if (mine) {
             const double *lwp = p.ln + (size_t)(4 * p.L + 2) * E;
@@ -615,18 +797,22 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
             of[0] = (double)f * (double)p.ochead[j];
             p.x[j] = sm.xown[ctid]; // residual stream after the last layer (debug / tests)
         }
-        publish_vparts<1>(vpartp(q), mx, of, rd, ctid);
+        publish_vparts<1>(vpartp(q), mx, of, rd, ctid, ne);
     }
+    stamp();
     grid_sync(p.gbar, target, ctid);
+    stamp();
     ++q;
-    rd.par = gather_quantise(sm, vecp(q - 1), vpartp(q - 1), 1, E, rd.par, ctid);
-    rp = consume_sub<CPL, FULL, 1>(p, sm, E, sl.v0, sl.v1, 0, 0, rp, warp, lane);
-    consumer_sync();
+    gather_quantise(sm.planes, sm.scal, vecp(q - 1), vpartp(q - 1), 1, E, ctid, p.trace);
+    stamp();
+    rp = consume_sub<CPL, FULL, kRowSplit>(c_ring, c_full, c_empty, (uint32_t)p.tile_bytes, (uint32_t)p.stages, c_planes + (uint32_t)(0), c_res + (uint32_t)(0) * 8u, E, sl.v0, sl.v1, rp, warp, lane, p.ptrace, c_tcnt);
+    tok_sync();
+    stamp();
     {
         float best = -INFINITY;
         int bidx = 0x7fffffff;
-        for (int i = ctid; i < sl.nv; i += kConsumers) {
-            const float y = (float)(sm.scal[0] * (double)sm.res64[i] + sm.scal[3]);
+        for (int i = ctid; i < sl.nv; i += kTokConsumers) {
+            const float y = (float)(sm.scal[0] * row_total(0, i, kRowSplit) + sm.scal[3]);
             p.logits[sl.v0 + i] = y;
             if (y > best) { // i ascending per thread: first maximum kept
                 best = y;
@@ -644,16 +830,16 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
                     bidx = oi;
                 }
             }
-            float *bv = reinterpret_cast<float *>(sm.scratch);
-            int *bi = reinterpret_cast<int *>(sm.scratch + 8);
-            consumer_sync();
+            float *bv = reinterpret_cast<float *>(sm.red);
+            int *bi = reinterpret_cast<int *>(sm.red + 16);
+            tok_sync();
             if (lane == 0) {
                 bv[warp] = best;
                 bi[warp] = bidx;
             }
-            consumer_sync();
+            tok_sync();
             if (ctid == 0) {
-                for (int w = 1; w < kConsumerWarps; ++w)
+                for (int w = 1; w < kTokWarps; ++w)
                     if (bv[w] > best || (bv[w] == best && bi[w] < bidx)) {
                         best = bv[w];
                         bidx = bi[w];
@@ -661,7 +847,9 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
                 p.amax_val[blockIdx.x] = best;
                 p.amax_idx[blockIdx.x] = bidx;
             }
-            grid_sync(p.gbar, target, ctid);
+            stamp();
+    grid_sync(p.gbar, target, ctid);
+    stamp();
             if (blockIdx.x == 0 && warp == 0) {
                 float b2 = -INFINITY;
                 int i2 = 0x7fffffff;

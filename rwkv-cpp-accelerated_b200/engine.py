@@ -160,6 +160,22 @@ class Engine:
             raise EngineError("debug_read(%s) failed" % name)
         return a
 
+    def read_trace(self, grid=148, per_cta=2048):
+        """Per-CTA globaltimer stamps of the last token kernel (set_option('trace', 1) first)."""
+        a = np.zeros(grid * per_cta, np.uint64)
+        got = self.lib.rwkv_b200_debug_read(self.h, b"trace", a.ctypes.data_as(ctypes.c_void_p), a.nbytes)
+        if got != a.size:
+            raise EngineError("read_trace failed (trace option not enabled?)")
+        return a.reshape(grid, per_cta)
+
+    def read_tile_trace(self, grid=148, per_cta=4096):
+        """[2][grid][per_cta] globaltimer: tile copy issued by the producer / tile seen ready by consumer thread 0."""
+        a = np.zeros(2 * grid * per_cta, np.uint64)
+        got = self.lib.rwkv_b200_debug_read(self.h, b"ptrace", a.ctypes.data_as(ctypes.c_void_p), a.nbytes)
+        if got != a.size:
+            raise EngineError("read_tile_trace failed")
+        return a.reshape(2, grid, per_cta)
+
     def decode_timed(self, tokens, teacher_forced=True):
         toks = np.ascontiguousarray(np.asarray(tokens, dtype=np.uint64))
         ms = ctypes.c_float()

@@ -1,0 +1,76 @@
+"""Phase-level timing of the persistent token kernel from %globaltimer stamps.
+usage: python trace_token.py [workload=7b]"""
+import importlib
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+
+pkg = importlib.import_module("rwkv-cpp-accelerated_b200")
+workload = sys.argv[1] if len(sys.argv) > 1 else "7b"
+L, E = bench.SHAPES[workload]
+eng = pkg.Engine(bench.model_path(workload, pkg))
+eng.set_option("trace", 1)
+tok = bench.SEED_TOKEN
+for _ in range(4):
+    tok = eng.forward_greedy(tok)
+tr = eng.read_trace().astype(np.int64)
+n = int((tr[0] > 0).sum())
+tr = tr[:, :n]
+t0 = tr[:, 0].min()
+tr = tr - t0
+print("stamps per CTA", n, "token time us", (tr[:, -1].max()) / 1e3)
+# stamp layout: 0 start | 1 E(embed) 2 B | per layer: [slice: E B][kvr: G C E B][out: G C E B][ffn slice: E B][rk: G C E B][v: G C E B] | head...
+names = []
+names += ["embed.epi", "embed.bar"]
+for l in range(L):
+    for ph in ("kvr", "out", "rk", "v"):
+        if ph in ("kvr", "rk"):
+            names += [("att_ln" if ph == "kvr" else "ffn_ln") + ".epi", ("att_ln" if ph == "kvr" else "ffn_ln") + ".bar"]
+        names += [ph + ".g_loads", ph + ".g_reduce", ph + ".g_quant", ph + ".g_sync", ph + ".gemv", ph + ".epi", ph + ".bar"]
+names += ["head_ln.epi", "head_ln.bar", "head.g_loads", "head.g_reduce", "head.g_quant", "head.g_sync", "head.gemv"]
+d = np.diff(tr, axis=1)  # [cta, n-1]
+agg = {}
+for i, nm in enumerate(names[:d.shape[1]]):
+    agg.setdefault(nm, []).append(d[:, i])
+print("%-12s %8s %8s %8s %8s   (us; mean over CTAs and layers, then min/max of per-CTA means)" % ("segment", "mean", "median", "min", "max"))
+tot = 0
+for nm, lst in agg.items():
+    a = np.stack(lst, 1) / 1e3  # [cta, layers]
+    per_layer = a.mean()
+    tot += a.mean(0).sum()
+    print("%-12s %8.2f %8.2f %8.2f %8.2f   x%d" % (nm, per_layer, np.median(a), a.mean(1).min(), a.mean(1).max(), a.shape[1]))
+print("sum of means (us):", tot)
+# arrival skew at barriers: spread of the stamp just before each barrier
+bar_idx = [i for i, nm in enumerate(names[:d.shape[1]]) if nm.endswith(".bar")]
+skew = [(tr[:, i].max() - tr[:, i].min()) / 1e3 for i in bar_idx]
+print("arrival skew at barriers (us): mean %.2f median %.2f max %.2f" % (np.mean(skew), np.median(skew), np.max(skew)))
+lat = [(tr[:, i + 1].min() - tr[:, i].max()) / 1e3 for i in bar_idx]
+print("barrier release latency after LAST arrival (us): mean %.2f median %.2f" % (np.mean(lat), np.median(lat)))
+
+# ---- tile-level: how far ahead of the consumers does the producer run? -------------------------
+tt = eng.read_tile_trace().astype(np.int64)
+issue, ready = tt[0, 0], tt[1, 0]  # CTA 0
+n_t = int((issue > 0).sum())
+issue, ready = (issue[:n_t] - t0) / 1e3, (ready[:n_t] - t0) / 1e3
+print("tiles per CTA:", n_t)
+lead = ready - issue
+print("issue->ready latency (us): median %.2f p10 %.2f p90 %.2f" % (np.median(lead), np.percentile(lead, 10), np.percentile(lead, 90)))
+# tiles issued but not yet consumed at each phase start (after each barrier stamp of CTA 0)
+bar_times = [tr[0, i + 1] / 1e3 for i, nm in enumerate(names[:d.shape[1]]) if nm.endswith(".bar")]
+ahead = [int((issue <= bt).sum() - (ready <= bt).sum()) for bt in bar_times[:60]]
+print("tiles in flight/resident at barrier exits (first 60):", ahead)
+k = 200
+print("sample tiles %d..%d: issue" % (k, k + 12), np.round(issue[k:k + 12], 1), "ready", np.round(ready[k:k + 12], 1))
+
+# full tile timeline of layer 2 (7B: 81 tiles per layer: K6 V6 R6 out6 ffnR6 ffnK23 ffnV28)
+per_layer = (n_t - 0) // (L + 1) if L else n_t
+base = 2 * 81
+print("layer-2 tiles: idx issue ready (us)")
+for i in range(base, min(base + 81, n_t)):
+    print("%4d %9.2f %9.2f  lag %.2f" % (i - base, issue[i], ready[i], ready[i] - issue[i]))
+print("layer-2 stamps (CTA 0, us):", np.round(tr[0, 3 + 2 * 32:3 + 3 * 32] / 1e3, 2))
