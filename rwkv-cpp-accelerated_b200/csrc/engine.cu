@@ -62,7 +62,6 @@ struct rwkv_b200_model {
     int sms = 0;
     int grid = 0;
     int cpl = 0;
-    int cpl_tok = 0;
     unsigned long long L = 0, E = 0, max_gpt = 1;
     cudaStream_t stream = nullptr;
     rk::Params p{};
@@ -116,9 +115,9 @@ template <int CPL> int set_attrs_tok(size_t smem) {
     CK(cudaFuncSetAttribute(rk::k_token<CPL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     return 0;
 }
-
-// One cooperative launch = one token (token_kernel.cuh). feed: 0 ctrl->token, 1 ctrl->next, 2 stream.
-template <int CPL> int launch_token_t(rwkv_b200_model *m, int feed, bool greedy, const unsigned long long *stream, cudaStream_t s);
+template <int CPL> const void *token_entry(bool full) {
+    return full ? (const void *)rk::k_token<CPL, true> : (const void *)rk::k_token<CPL, false>;
+}
 
 struct EventPair {
     cudaEvent_t a, b;
@@ -170,33 +169,28 @@ int launch_one(M *m, int cls, int layer, cudaStream_t s, Prof *prof) {
     return 0;
 }
 
-template <int CPL> int launch_token_t(M *m, int feed, bool greedy, const unsigned long long *stream, cudaStream_t s) {
+// Ring geometry per mode. Token kernel: a tile is eight row segments of n_embed bytes (one per
+// consumer warp); staged kernels: 20 KB tiles. As many stages as fit beside the limb planes.
+void configure_mode(M *m) {
+    rk::Params &p = m->p;
+    p.tile_bytes = m->token_mode ? (int)(8 * m->E) : 20480;
+    if (p.tile_bytes < (int)(4 * m->E)) p.tile_bytes = (int)(4 * m->E);
+    p.stages = (int)std::min<size_t>(rk::kMaxStages, (232448 - rk::smem_bytes(0, 0, p.plane_cap)) / p.tile_bytes);
+    m->smem = rk::smem_bytes(p.stages, p.tile_bytes, p.plane_cap);
+}
+
+int launch_token(M *m, int feed, bool greedy, const unsigned long long *stream, cudaStream_t s) {
     rk::Params prm = m->p;
     prm.L_run = layers_to_run(m);
     prm.feed_mode = feed;
     prm.greedy = greedy ? 1 : 0;
     prm.stream = stream;
     void *args[] = {&prm};
-    const void *fn = (m->E == (unsigned long long)CPL * 512 * rk::kRowSplit) ? (const void *)rk::k_token<CPL, true> : (const void *)rk::k_token<CPL, false>;
+    const bool full = m->E == (unsigned long long)m->cpl * 512ull;
+    const void *fn = m->cpl == 2 ? token_entry<2>(full) : m->cpl == 4 ? token_entry<4>(full)
+                   : m->cpl == 8 ? token_entry<8>(full) : token_entry<10>(full);
     CK(cudaLaunchCooperativeKernel(fn, dim3(m->grid), dim3(rk::kTokThreads), args, m->smem, s));
     return 0;
-}
-
-int launch_token(M *m, int feed, bool greedy, const unsigned long long *stream, cudaStream_t s) {
-    switch (m->cpl_tok) { // 16-byte chunks per lane of one row segment (n_embed / kRowSplit bytes)
-#if RK_TOK_WARPS == 16
-    case 1: return launch_token_t<1>(m, feed, greedy, stream, s);
-    case 2: return launch_token_t<2>(m, feed, greedy, stream, s);
-    case 4: return launch_token_t<4>(m, feed, greedy, stream, s);
-    case 5: return launch_token_t<5>(m, feed, greedy, stream, s);
-#else
-    case 2: return launch_token_t<2>(m, feed, greedy, stream, s);
-    case 4: return launch_token_t<4>(m, feed, greedy, stream, s);
-    case 8: return launch_token_t<8>(m, feed, greedy, stream, s);
-    case 10: return launch_token_t<10>(m, feed, greedy, stream, s);
-#endif
-    default: return fail(3, "unsupported chunks-per-lane %d", m->cpl_tok);
-    }
 }
 
 // The kernel sequence of one token.
@@ -371,22 +365,16 @@ int do_load(M *m, const char *path, int quiet) {
     CK(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
 
     m->cpl = E <= 1024 ? 2 : E <= 2048 ? 4 : E <= 4096 ? 8 : 10;
-    {
-        const unsigned long long seg = E / rk::kRowSplit;
-        m->cpl_tok = seg <= 512 ? 1 : seg <= 1024 ? 2 : seg <= 2048 ? 4 : seg <= 2560 ? 5 : seg <= 4096 ? 8 : 10;
-        if (rk::kRowSplit == 1 && m->cpl_tok == 1) m->cpl_tok = 2;
-        if (rk::kRowSplit == 1 && m->cpl_tok == 5) m->cpl_tok = 8;
-        if (E % (16 * rk::kRowSplit) != 0) m->token_mode = false; // segments must be whole 16-byte chunks
+    if (const char *e = getenv("RWKV_B200_MODE")) {
+        if (std::string(e) == "staged") m->token_mode = false;
     }
     rk::Params &p = m->p;
     p.L = (int)L;
     p.E = (int)E;
-    p.tile_bytes = 20480;
     p.plane_cap = (int)(12 * E);
-    p.stages = (int)std::min<size_t>(rk::kMaxStages, (232448 - rk::smem_bytes(0, 0, p.plane_cap)) / p.tile_bytes);
+    configure_mode(m);
     p.tp_rank = m->tp_rank;
     p.tp_size = m->tp_size;
-    m->smem = rk::smem_bytes(p.stages, p.tile_bytes, p.plane_cap);
     if ((4 * E + m->grid - 1) / m->grid + (E + m->grid - 1) / m->grid + 2 > (unsigned long long)rk::kMaxRowsPerCta ||
         (E + m->grid - 1) / m->grid + 1 > (unsigned long long)rk::kMaxSlice ||
         (4 * E + m->grid - 1) / m->grid + 1 > 2ull * rk::kConsumers ||
@@ -394,24 +382,10 @@ int do_load(M *m, const char *path, int quiet) {
         m->grid > rk::kRedMax || (4 * E + m->grid - 1) / m->grid + 1 > (unsigned long long)rk::kRedMax)
         return fail(5, "grid of %d CTAs is too small for n_embed=%llu", m->grid, E);
     switch (m->cpl) {
-    case 2: rc = set_attrs<2>(m->smem); break;
-    case 4: rc = set_attrs<4>(m->smem); break;
-    case 8: rc = set_attrs<8>(m->smem); break;
-    default: rc = set_attrs<10>(m->smem); break;
-    }
-    if (rc) return rc;
-    switch (m->cpl_tok) {
-#if RK_TOK_WARPS == 16
-    case 1: rc = set_attrs_tok<1>(m->smem); break;
-    case 2: rc = set_attrs_tok<2>(m->smem); break;
-    case 4: rc = set_attrs_tok<4>(m->smem); break;
-    default: rc = set_attrs_tok<5>(m->smem); break;
-#else
-    case 2: rc = set_attrs_tok<2>(m->smem); break;
-    case 4: rc = set_attrs_tok<4>(m->smem); break;
-    case 8: rc = set_attrs_tok<8>(m->smem); break;
-    default: rc = set_attrs_tok<10>(m->smem); break;
-#endif
+    case 2: rc = set_attrs<2>(232448), rc = rc ? rc : set_attrs_tok<2>(232448); break;
+    case 4: rc = set_attrs<4>(232448), rc = rc ? rc : set_attrs_tok<4>(232448); break;
+    case 8: rc = set_attrs<8>(232448), rc = rc ? rc : set_attrs_tok<8>(232448); break;
+    default: rc = set_attrs<10>(232448), rc = rc ? rc : set_attrs_tok<10>(232448); break;
     }
     if (rc) return rc;
 
@@ -501,7 +475,7 @@ int do_load(M *m, const char *path, int quiet) {
     {
         int coop = 0;
         CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, m->device));
-        if (!coop) m->token_mode = false;
+        if (!coop && m->token_mode) return fail(6, "device does not support cooperative launch");
     }
     CK(cudaMemsetAsync(p.x, 0, E * sizeof(double), m->stream));
     m->tensors[X] = p.x;
@@ -832,17 +806,18 @@ int rwkv_b200_set_option(rwkv_b200_model *m, const char *key, const char *value)
             cudaMemset(t, 0, (size_t)rk::kMaxGrid * rk::kTraceMax * 8);
             m->p.trace = t;
             unsigned long long *pt = nullptr;
-            if (dmalloc(m, &pt, (size_t)2 * rk::kRedMax * rk::kTileTraceMax)) return fail(1, "trace alloc failed");
-            cudaMemset(pt, 0, (size_t)2 * rk::kRedMax * rk::kTileTraceMax * 8);
+            if (dmalloc(m, &pt, (size_t)3 * rk::kRedMax * rk::kTileTraceMax)) return fail(1, "trace alloc failed");
+            cudaMemset(pt, 0, (size_t)3 * rk::kRedMax * rk::kTileTraceMax * 8);
             m->p.ptrace = pt;
         } else if (!v) {
             m->p.trace = nullptr;
             m->p.ptrace = nullptr;
         }
     } else if (k == "mode") {
-        if (std::string(value) == "token") m->token_mode = true;
-        else if (std::string(value) == "staged") m->token_mode = false;
-        else return fail(1, "mode must be 'token' or 'staged'");
+        const bool want_token = std::string(value) == "token";
+        if (!want_token && std::string(value) != "staged") return fail(1, "mode must be 'token' or 'staged'");
+        m->token_mode = want_token;
+        configure_mode(m);
     }
     else if (k == "max_layers") m->max_layers = v;
     else if (k == "stages") {
@@ -852,6 +827,7 @@ int rwkv_b200_set_option(rwkv_b200_model *m, const char *key, const char *value)
         m->p.stages = v;
         m->smem = smem;
     } else if (k == "tile_bytes") {
+        if (m->token_mode) return fail(1, "the token kernel's tile is fixed at 8*n_embed bytes");
         if (v < (int)(4 * m->E) || v % 16) return fail(1, "tile_bytes must be a multiple of 16 and >= 4*n_embed");
         int st = m->p.stages;
         while (st > 2 && rk::smem_bytes(st, v, m->p.plane_cap) > 232448) --st;
@@ -884,7 +860,7 @@ long long rwkv_b200_debug_read(rwkv_b200_model *m, const char *name, void *dst, 
     else if (k == "xs_v") src = m->p.xs_v, count = 4 * E, bytes = 16 * E;
     else if (k == "logits") src = m->p.logits, count = binfmt::kVocab, bytes = 4 * binfmt::kVocab;
     else if (k == "trace" && m->p.trace) src = m->p.trace, count = (size_t)m->grid * rk::kTraceMax, bytes = count * 8;
-    else if (k == "ptrace" && m->p.ptrace) src = m->p.ptrace, count = (size_t)2 * m->grid * rk::kTileTraceMax, bytes = count * 8;
+    else if (k == "ptrace" && m->p.ptrace) src = m->p.ptrace, count = (size_t)3 * m->grid * rk::kTileTraceMax, bytes = count * 8;
     else return -1;
     if (dst_bytes < bytes) return -1;
     if (cudaStreamSynchronize(m->stream) != cudaSuccess) return -1;

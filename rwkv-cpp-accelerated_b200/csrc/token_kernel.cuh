@@ -27,27 +27,72 @@ namespace rk {
 
 // ---- thread layout of the token kernel -------------------------------------------------------
 // Four consumer warpgroups (16 warps) + one producer warpgroup (warp 16 streams weights; its
-// other three warps only donate registers). Every weight row is cut into kRowSplit segments
+// other three warps only donate registers). Every weight row is cut into 1 segments
 // handled by different warps, so a lane holds the limbs of only E/2 inputs: registers per thread
 // halve versus one-warp-per-row, which is what makes four warps per scheduler possible; that
 // occupancy is needed to hide LDS / IDP / REDUX latency in the GEMV core and to run the
 // phase-boundary code at a reasonable IPC. setmaxnreg moves the producer warpgroup's registers
 // to the consumers (40 vs 104; the compile-time budget of a 640-thread CTA is 96).
+#ifndef RK_PIPE
+#define RK_PIPE 0
+#endif
+#ifndef RK_PIN
+#define RK_PIN 0
+#endif
+#ifndef RK_CORE_INLINE
+#define RK_CORE_INLINE __forceinline__
+#endif
+#ifndef RK_GATHER_INLINE
+#define RK_GATHER_INLINE __noinline__
+#endif
 #ifndef RK_TOK_WARPS
 #define RK_TOK_WARPS 8
 #endif
 constexpr int kTokWarps = RK_TOK_WARPS;       // 8: one warp per row, 232 regs; 16: two warps per row, 104 regs
 constexpr int kTokConsumers = kTokWarps * 32;
-constexpr int kTokThreads = kTokConsumers + 128;
+#ifndef RK_PRODUCER_THREADS
+#define RK_PRODUCER_THREADS 128
+#endif
+// The producer is a whole warpgroup (one lane of it works) so that setmaxnreg can hand its
+// registers to the consumers: 384 threads compile to a budget of 168, consumers then take 232.
+// (A 288-thread CTA does not help: 9 warps put 3 on one scheduler, 16384/96 = 170 registers.)
+// ptxas still makes its pre-allocation choices against 168: left alone it re-derives thread ids,
+// shared-window bases and kernel parameters inside every tile iteration and keeps one shared
+// load in flight (ncu r01d: 45 % of the core's samples). The hot loop therefore takes its
+// operands through opaque() - values the optimiser cannot rematerialise - and pins its loads.
+constexpr int kProducerThreads = RK_PRODUCER_THREADS;
+constexpr int kTokThreads = kTokConsumers + kProducerThreads;
 constexpr int kProducerRegs = 40;
 // setmaxnreg budget: the consumers may only take what the producer warpgroup gives back
 // (16 warps: compile budget 96, 4 WG x 128 x (104-96) = 4096 <= 128 x (96-40); 8 warps: 168 -> 232).
 constexpr int kConsumerRegs = kTokWarps == 8 ? 232 : 104;
-constexpr int kRowSplit = kTokWarps / 8;      // segments per E-byte row (4E-byte rows: 4 * kRowSplit)
-constexpr int kTokMaxRows = 1024;             // res64 capacity: (rows of one CTA) * segments
 
 __device__ __forceinline__ void tok_sync() { // named barrier 1: the 16 consumer warps
     asm volatile("bar.sync 1, %0;" ::"n"(kTokConsumers) : "memory");
+}
+
+// Identity the optimiser cannot see through. The layer loop reads ~35 per-layer arrays at
+// base + l*E + j; left alone, strength reduction turns every one of them into its own 64-bit
+// induction pointer that stays live through the GEMV core (measured: 115 registers live across
+// the core, which then has none left to keep more than one shared-memory load in flight).
+__device__ __forceinline__ int opaque(int v) {
+    asm volatile("" : "+r"(v));
+    return v;
+}
+__device__ __forceinline__ uint32_t opaque(uint32_t v) {
+    asm volatile("" : "+r"(v));
+    return v;
+}
+__device__ __forceinline__ size_t opaque(size_t v) {
+    asm volatile("" : "+l"(v));
+    return v;
+}
+
+// two 16-byte shared loads 512 bytes apart in one asm block (keeps them adjacent in the schedule)
+__device__ __forceinline__ void lds128x2(uint32_t addr, uint4 &a, uint4 &b) {
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%8];\n\tld.shared.v4.u32 {%4,%5,%6,%7}, [%8+512];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+                 : "r"(addr));
 }
 
 // weights (signed bytes) x activation digits (unsigned bytes)
@@ -132,53 +177,107 @@ struct RingPos {
     }
 };
 
+// ---- row-major streaming ---------------------------------------------------------------------
+// Weights are row-major [out][in] int8. A tile is exactly eight work units: a unit is one row
+// segment of SEG = n_embed bytes (rows of E bytes: one unit per row, eight rows per tile; rows of
+// 4E bytes: four units per row, two rows per tile), so consumer warp w always takes unit w of
+// every tile - no dealing logic, no divisions in the loop. The activation limbs of a warp's
+// segment live in its registers (CPL 16-byte chunks per lane x 3 planes).
+// Measured in tools/ringbench.cu (same loop, L2-resident source): 49-52 B/clk/SM, 2.2x the HBM
+// rate; tools/corebench.cu: 64 B/clk/SM for the bare loop. The "lane = row" alternative
+// (activations broadcast from shared memory) is capped at 35-42 B/clk/SM by shared-memory
+// bandwidth - a broadcast LDS.128 still writes 512 B of registers.
+// One issuing lane. Several lanes taking tiles round-robin measured no faster (tools/ringbench.cu)
+// and are unsafe: a lane two ring passes ahead aliases the parity of the empty barrier.
+constexpr int kProducers = 1;
+
 __device__ __forceinline__ void produce_sub(const Params &p, const Smem &sm, const int8_t *base, int N, int r0, int r1,
-                                            RingPos &rp, uint64_t policy, int &tcount) {
-    int tr = p.tile_bytes / N;
-    if (tr < 1) tr = 1;
+                                            RingPos &rp, uint64_t policy, int &tcount, int pw) {
     const uint32_t ring = smem_u32(sm.ring);
     const uint32_t full0 = smem_u32(sm.full), empty0 = smem_u32(sm.empty);
+    const int tr = (8 * p.E) / N; // rows per tile: 8 (N = E) or 2 (N = 4E)
     for (int r = r0; r < r1; r += tr) {
-        const int rows = min(tr, r1 - r);
-        const uint32_t bytes = (uint32_t)rows * (uint32_t)N;
-        // first pass over the ring: a fresh mbarrier reports the "previous" phase as complete
-        mbar_wait(empty0 + 8 * rp.stage, rp.phase ^ 1);
-        const uint32_t fb = full0 + 8 * rp.stage;
-        mbar_expect_tx(fb, bytes);
-        bulk_g2s(ring + rp.stage * (uint32_t)p.tile_bytes, base + (size_t)r * N, bytes, fb, policy);
-        if (p.ptrace != nullptr && tcount < kTileTraceMax) {
-            unsigned long long t;
-            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-            p.ptrace[(size_t)blockIdx.x * kTileTraceMax + tcount] = t;
+        if ((tcount & (kProducers - 1)) == pw) {
+            const uint32_t bytes = (uint32_t)(min(tr, r1 - r) * N);
+            // first pass over the ring: a fresh mbarrier reports the "previous" phase as complete
+            mbar_wait(empty0 + 8 * rp.stage, rp.phase ^ 1);
+            const uint32_t fb = full0 + 8 * rp.stage;
+            mbar_expect_tx(fb, bytes);
+            bulk_g2s(ring + rp.stage * (uint32_t)p.tile_bytes, base + (size_t)r * N, bytes, fb, policy);
+            if (p.ptrace != nullptr && tcount < kTileTraceMax) {
+                unsigned long long t;
+                asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+                p.ptrace[(size_t)blockIdx.x * kTileTraceMax + tcount] = t;
+            }
         }
         ++tcount;
         rp.advance((uint32_t)p.stages);
     }
 }
 
-// Consumer side of one streamed sub-matrix. Work units (row, segment) are dealt round-robin to the
-// eight warps across tile boundaries, so tiles may hold any number of rows. NSEG == 1: one warp
-// per row, exact row total -> res64[res_off + row]; NSEG == 4 (rows of 4E bytes): four warps per
-// row, one E-byte segment each, segment totals -> res64[res_off + row*4 + seg] (summed by the
-// epilogue; no atomics).
-// Everything the GEMV core needs, as plain values (shared-space addresses are 32-bit): a noinline
-// function that takes the Smem struct by reference re-reads its fields from LOCAL memory, and with
-// 227 KB of the unified L1/shared array carved out as shared memory every such access is an L2
-// round trip - measured as a ~1300-cycle fixed cost per row.
-struct CoreArgs {
-    uint32_t ring, full0, empty0; // shared addresses
-    uint32_t tile_bytes, stages;
-    unsigned long long *ptrace;   // tile-ready trace (debug) or nullptr
-    int *tile_cnt;                // shared-memory tile counter of the trace
-};
+// Consumer side of one streamed sub-matrix. All arguments are plain values in registers (a
+// noinline function that takes the Smem struct by reference re-reads its fields from LOCAL memory,
+// and with 227 KB of shared memory carved out there is no L1 to catch that).
+// NSEG = N / E (1 or 4). planes: shared address of limb plane 0 of this sub's activation vector
+// (planes 1, 2 at +N, +2N); res: shared address of this sub's int64 [row][NSEG] partial totals.
+// Half of a unit's weight bytes -> registers: chunks [HALF*H, HALF*H + H) of the lane.
+template <int H, int HALF, bool FULL>
+__device__ __forceinline__ void load_half(uint4 (&w)[H], uint32_t row, int lane, int nchunks) {
+#pragma unroll
+    for (int i = 0; i < H; ++i) {
+        if (FULL || lane + 32 * (HALF * H + i) < nchunks) w[i] = lds128(row + (HALF * H + i) * 512);
+        else w[i] = make_uint4(0, 0, 0, 0);
+    }
+}
 
+// Exact int32 dot products of half a unit against the three limb planes (two chains per plane).
+template <int CPL, int H, int HALF>
+__device__ __forceinline__ void dot_half(const uint4 (&w)[H], const uint4 (&a0)[CPL], const uint4 (&a1)[CPL],
+                                         const uint4 (&a2)[CPL], int (&acc)[6]) {
+#pragma unroll
+    for (int i = 0; i < H; ++i) {
+        constexpr int o = HALF * H;
+        acc[0] = dp4a_su(w[i].x, a0[o + i].x, acc[0]);
+        acc[2] = dp4a_su(w[i].x, a1[o + i].x, acc[2]);
+        acc[4] = dp4a_ss(w[i].x, a2[o + i].x, acc[4]);
+        acc[1] = dp4a_su(w[i].y, a0[o + i].y, acc[1]);
+        acc[3] = dp4a_su(w[i].y, a1[o + i].y, acc[3]);
+        acc[5] = dp4a_ss(w[i].y, a2[o + i].y, acc[5]);
+        acc[0] = dp4a_su(w[i].z, a0[o + i].z, acc[0]);
+        acc[2] = dp4a_su(w[i].z, a1[o + i].z, acc[2]);
+        acc[4] = dp4a_ss(w[i].z, a2[o + i].z, acc[4]);
+        acc[1] = dp4a_su(w[i].w, a0[o + i].w, acc[1]);
+        acc[3] = dp4a_su(w[i].w, a1[o + i].w, acc[3]);
+        acc[5] = dp4a_ss(w[i].w, a2[o + i].w, acc[5]);
+    }
+}
+
+// Consumer side of one streamed sub-matrix, software-pipelined in half-units: while a warp runs
+// the dot products of one half of its row segment, the shared-memory loads of the other half -
+// or of the first half of the NEXT tile, which has usually landed already - are in flight.
+// With two warps per scheduler, all eight in step on the same tile, nothing else hides the load
+// phase (32 KB of LDS per tile = 256 clk of shared-memory bandwidth) behind the 384 clk of IDP.4A.
+// The __syncwarp()s pin that order: memory operations may not move across a warp barrier, and
+// ptxas otherwise sinks every load next to its first use (one exposed LDS latency per 16 bytes).
+// NSEG = N / E (1 or 4). planes: shared address of limb plane 0 of this sub's activation vector
+// (planes 1, 2 at +N, +2N); res: shared address of this sub's int64 [row][NSEG] partial totals.
 template <int CPL, bool FULL, int NSEG>
-__device__ __noinline__ RingPos consume_sub(uint32_t ring, uint32_t full0, uint32_t empty0, uint32_t tile_bytes,
-                                            uint32_t stages, uint32_t planes, uint32_t res, int N, int r0, int r1,
-                                            RingPos rp, int warp, int lane, unsigned long long *ptrace, int *tile_cnt) {
+__device__ RK_CORE_INLINE RingPos consume_sub(uint32_t ring, uint32_t full0, uint32_t empty0, uint32_t tile_bytes,
+                                            uint32_t stages, uint32_t planes, uint32_t res, int N, int nr, RingPos rp,
+                                            int warp, int lane, unsigned long long *ptrace, int *tile_cnt) {
+    static_assert(CPL % 2 == 0, "chunks per lane must be even");
+    constexpr int TR = 8 / NSEG; // rows per tile
+    constexpr int H = CPL / 2;
     const int seg_len = N / NSEG;
     const int nchunks = seg_len >> 4;
-    const int seg = warp % NSEG;
+    const int seg = warp % NSEG, rl = warp / NSEG; // this warp's unit inside every tile
+    const uint32_t unit_off = (uint32_t)(rl * N + seg * seg_len + lane * 16);
+    const int ntiles = (nr + TR - 1) / TR;
+    if (ntiles <= 0) return rp;
+#if RK_PIPE
+    uint4 h0[H], h1[H];
+    mbar_wait(full0 + 8 * rp.stage, rp.phase);
+    if (rl < nr) load_half<H, 0, FULL>(h0, ring + rp.stage * tile_bytes + unit_off, lane, nchunks);
     uint4 a0[CPL], a1[CPL], a2[CPL];
     {
         const uint32_t pl = planes + (uint32_t)(seg * seg_len);
@@ -194,67 +293,108 @@ __device__ __noinline__ RingPos consume_sub(uint32_t ring, uint32_t full0, uint3
             }
         }
     }
-    int tr = (int)tile_bytes / N;
-    if (tr < 1) tr = 1;
-    const uint32_t lane_off = (uint32_t)(seg * seg_len + lane * 16);
-    int ubase = 0; // units handed out so far in this sub (mod kTokWarps); always a multiple of NSEG
-    for (int r = r0; r < r1; r += tr) {
-        const int rows = min(tr, r1 - r);
+    uint32_t dst = res + (uint32_t)((rl * NSEG + seg) * 8);
+    int row = rl; // this warp's row (relative to the sub) in the current tile
+    for (int t = 0; t < ntiles; ++t) {
+        const bool mine = row < nr, have_next = t + 1 < ntiles;
+        RingPos nx = rp;
+        nx.advance(stages);
+        if (mine) load_half<H, 1, FULL>(h1, ring + rp.stage * tile_bytes + unit_off, lane, nchunks);
+        __syncwarp();
+        if (ptrace != nullptr && threadIdx.x == 0) { // trace row [1]: %globaltimer when warp 0 starts on the tile
+            const int c = *tile_cnt;
+            if (c < kTileTraceMax) {
+                unsigned long long tm;
+                asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tm));
+                ptrace[((size_t)gridDim.x + blockIdx.x) * kTileTraceMax + c] = tm;
+            }
+            *tile_cnt = c + 1;
+        }
+        int acc[6] = {0, 0, 0, 0, 0, 0};
+        if (mine) dot_half<CPL, H, 0>(h0, a0, a1, a2, acc);
+        // one poll: if the next tile has landed, start on it before the second half's arithmetic
+        bool pre = false;
+        if (have_next) {
+            pre = __all_sync(0xffffffffu, mbar_try_wait(full0 + 8 * nx.stage, nx.phase));
+            if (pre && row + TR < nr) load_half<H, 0, FULL>(h0, ring + nx.stage * tile_bytes + unit_off, lane, nchunks);
+        }
+        __syncwarp();
+        if (mine) {
+            dot_half<CPL, H, 1>(h1, a0, a1, a2, acc);
+            const int t0 = __reduce_add_sync(0xffffffffu, acc[0] + acc[1]);
+            const int t1 = __reduce_add_sync(0xffffffffu, acc[2] + acc[3]);
+            const int t2 = __reduce_add_sync(0xffffffffu, acc[4] + acc[5]);
+            if (lane == 0) {
+                const long long tot = (((long long)t2 << 8) + (long long)t1) * 256 + (long long)t0;
+                asm volatile("st.shared.u64 [%0], %1;" ::"r"(dst), "l"(tot) : "memory");
+            }
+        }
+        dst += 8 * 8; // eight units per tile
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty0 + 8 * rp.stage);
+        if (have_next && !pre) {
+            mbar_wait(full0 + 8 * nx.stage, nx.phase);
+            if (row + TR < nr) load_half<H, 0, FULL>(h0, ring + nx.stage * tile_bytes + unit_off, lane, nchunks);
+        }
+        row += TR;
+        rp = nx;
+    }
+#else
+    uint4 a0[CPL], a1[CPL], a2[CPL];
+    {
+        const uint32_t pl = planes + (uint32_t)(seg * seg_len);
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) {
+            const int c = lane + 32 * i;
+            if (FULL || c < nchunks) {
+                a0[i] = lds128(pl + c * 16);
+                a1[i] = lds128(pl + N + c * 16);
+                a2[i] = lds128(pl + 2 * N + c * 16);
+            } else {
+                a0[i] = a1[i] = a2[i] = make_uint4(0, 0, 0, 0);
+            }
+        }
+    }
+    uint32_t dst = res + (uint32_t)((rl * NSEG + seg) * 8);
+    int row = rl;
+    for (int t = 0; t < ntiles; ++t) {
         mbar_wait(full0 + 8 * rp.stage, rp.phase);
         if (ptrace != nullptr && threadIdx.x == 0) {
             const int c = *tile_cnt;
             if (c < kTileTraceMax) {
-                unsigned long long t;
-                asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-                ptrace[((size_t)gridDim.x + blockIdx.x) * kTileTraceMax + c] = t;
+                unsigned long long tm;
+                asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tm));
+                ptrace[((size_t)gridDim.x + blockIdx.x) * kTileTraceMax + c] = tm;
             }
             *tile_cnt = c + 1;
         }
-        const uint32_t tile = ring + rp.stage * tile_bytes + lane_off;
-        const int units = rows * NSEG;
-        for (int u = (warp - ubase) & (kTokWarps - 1); u < units; u += kTokWarps) {
-            const int rl = u / NSEG;
-            const uint32_t row = tile + (uint32_t)(rl * N);
-            // all loads of the row segment first, then the arithmetic: keeps CPL 128-bit LDS in flight
-            uint4 w[CPL];
-#pragma unroll
-            for (int i = 0; i < CPL; ++i) {
-                if (FULL || lane + 32 * i < nchunks) w[i] = lds128(row + i * 512);
-                else w[i] = make_uint4(0, 0, 0, 0);
-            }
-            int s0a = 0, s0b = 0, s1a = 0, s1b = 0, s2a = 0, s2b = 0;
-#pragma unroll
-            for (int i = 0; i < CPL; ++i) {
-                s0a = dp4a_su(w[i].x, a0[i].x, s0a);
-                s1a = dp4a_su(w[i].x, a1[i].x, s1a);
-                s2a = dp4a_ss(w[i].x, a2[i].x, s2a);
-                s0b = dp4a_su(w[i].y, a0[i].y, s0b);
-                s1b = dp4a_su(w[i].y, a1[i].y, s1b);
-                s2b = dp4a_ss(w[i].y, a2[i].y, s2b);
-                s0a = dp4a_su(w[i].z, a0[i].z, s0a);
-                s1a = dp4a_su(w[i].z, a1[i].z, s1a);
-                s2a = dp4a_ss(w[i].z, a2[i].z, s2a);
-                s0b = dp4a_su(w[i].w, a0[i].w, s0b);
-                s1b = dp4a_su(w[i].w, a1[i].w, s1b);
-                s2b = dp4a_ss(w[i].w, a2[i].w, s2b);
-            }
-            const int t0 = __reduce_add_sync(0xffffffffu, s0a + s0b);
-            const int t1 = __reduce_add_sync(0xffffffffu, s1a + s1b);
-            const int t2 = __reduce_add_sync(0xffffffffu, s2a + s2b);
+        if (row < nr) {
+            const uint32_t wrow = ring + rp.stage * tile_bytes + unit_off;
+            uint4 h0[H], h1[H];
+            load_half<H, 0, FULL>(h0, wrow, lane, nchunks);
+            load_half<H, 1, FULL>(h1, wrow, lane, nchunks);
+#if RK_PIN
+            __syncwarp();
+#endif
+            int acc[6] = {0, 0, 0, 0, 0, 0};
+            dot_half<CPL, H, 0>(h0, a0, a1, a2, acc);
+            dot_half<CPL, H, 1>(h1, a0, a1, a2, acc);
+            const int t0 = __reduce_add_sync(0xffffffffu, acc[0] + acc[1]);
+            const int t1 = __reduce_add_sync(0xffffffffu, acc[2] + acc[3]);
+            const int t2 = __reduce_add_sync(0xffffffffu, acc[4] + acc[5]);
             if (lane == 0) {
                 const long long tot = (((long long)t2 << 8) + (long long)t1) * 256 + (long long)t0;
-                const uint32_t dst = res + (uint32_t)((((r - r0) + rl) * NSEG + seg) * 8);
                 asm volatile("st.shared.u64 [%0], %1;" ::"r"(dst), "l"(tot) : "memory");
             }
         }
-        ubase = (ubase + units) & (kTokWarps - 1);
+        dst += 8 * 8;
+        row += TR;
         __syncwarp();
         if (lane == 0) mbar_arrive(empty0 + 8 * rp.stage);
-        if (++rp.stage == stages) {
-            rp.stage = 0;
-            rp.phase ^= 1;
-        }
+        rp.advance(stages);
     }
+#endif
+    // leave the ring position after the last tile of this sub
     return rp;
 }
 
@@ -276,22 +416,22 @@ __device__ __forceinline__ Slices make_slices(int E) {
 }
 
 // The producer's whole-token schedule. MUST enumerate subs in exactly the consumers' order.
-__device__ __forceinline__ void produce_token(const Params &p, const Smem &sm, const Slices &sl) {
+__device__ __forceinline__ void produce_token(const Params &p, const Smem &sm, const Slices &sl, int pw) {
     const uint64_t pol = policy_evict_first();
     const int E = p.E;
     RingPos rp{0, 0};
     int tcount = 0;
     for (int l = 0; l < p.L_run; ++l) {
         const size_t mo = (size_t)l * E * E;
-        produce_sub(p, sm, p.wk + mo, E, sl.e0, sl.e1, rp, pol, tcount);
-        produce_sub(p, sm, p.wv + mo, E, sl.e0, sl.e1, rp, pol, tcount);
-        produce_sub(p, sm, p.wr + mo, E, sl.e0, sl.e1, rp, pol, tcount);
-        produce_sub(p, sm, p.wo + mo, E, sl.e0, sl.e1, rp, pol, tcount);
-        produce_sub(p, sm, p.wfr + mo, E, sl.e0, sl.e1, rp, pol, tcount);
-        produce_sub(p, sm, p.wfk + 4 * mo, E, sl.k0, sl.k1, rp, pol, tcount);
-        produce_sub(p, sm, p.wfv + 4 * mo, 4 * E, sl.e0, sl.e1, rp, pol, tcount);
+        produce_sub(p, sm, p.wk + mo, E, sl.e0, sl.e1, rp, pol, tcount, pw);
+        produce_sub(p, sm, p.wv + mo, E, sl.e0, sl.e1, rp, pol, tcount, pw);
+        produce_sub(p, sm, p.wr + mo, E, sl.e0, sl.e1, rp, pol, tcount, pw);
+        produce_sub(p, sm, p.wo + mo, E, sl.e0, sl.e1, rp, pol, tcount, pw);
+        produce_sub(p, sm, p.wfr + mo, E, sl.e0, sl.e1, rp, pol, tcount, pw);
+        produce_sub(p, sm, p.wfk + 4 * mo, E, sl.k0, sl.k1, rp, pol, tcount, pw);
+        produce_sub(p, sm, p.wfv + 4 * mo, 4 * E, sl.e0, sl.e1, rp, pol, tcount, pw);
     }
-    produce_sub(p, sm, p.whead, E, sl.v0, sl.v1, rp, pol, tcount);
+    produce_sub(p, sm, p.whead, E, sl.v0, sl.v1, rp, pol, tcount, pw);
 }
 
 // mean / std of the full residual stream from the per-CTA partial sums, with the reference's f32
@@ -399,33 +539,22 @@ __device__ __forceinline__ void trace_stamp2(unsigned long long *trace, double *
 }
 
 // After a barrier: fetch every CTA's partials and the `nvec` activation vectors of length N
-// (vector v -> limb planes at offset v*3*N), one block reduction, then quantise from registers.
-// All loads (up to 24 x 16 B per thread) are issued before anything is consumed, so the whole
-// gather costs ONE L2 round trip; every CTA walks the vector from a different starting offset so
-// that the 148 CTAs do not hit the same L2 lines at the same moment.
-constexpr int kGatherBatches = kTokWarps == 8 ? 6 : 3; // x 4 float4 groups x threads x 4 elements >= 4*5120
-__device__ __noinline__ void gather_quantise(uint8_t *planes, double *scal, const float *vec, const double *vpart,
+// (vector v -> limb planes at offset v*3*N), reduce the partials, then quantise from registers.
+// Warp 0 loads and reduces the per-CTA partials; warps 1.. load the vectors (up to 24 x 16 B per
+// thread) - everything is issued before anything is consumed, so the whole gather costs ONE L2
+// round trip. The two roles keep their loads in disjoint register sets of the same function; when
+// every warp did both, the 96 + 60 registers spilled and each spill store waited for its load
+// (ncu r01d: 6 % of all samples on STL). Every CTA walks the vector from a different starting
+// offset so that the 148 CTAs do not hit the same L2 lines at the same moment.
+constexpr int kGatherBatches = 6;                 // x 4 float4 groups x 224 threads x 4 elements >= 4*5120
+constexpr int kGatherThreads = kTokConsumers - 32; // warps 1..7
+__device__ RK_GATHER_INLINE void gather_quantise(uint8_t *planes, double *scal, const float *vec, const double *vpart,
                                              int nvec, int N, int ctid, unsigned long long *trace) {
-    const int ng = N >> 2;                                       // float4 groups per vector
-    const int nb = (ng + 4 * kTokConsumers - 1) / (4 * kTokConsumers); // batches of 4 groups per thread per vector
-    const int total = nvec * nb;                                 // <= kGatherBatches
+    const int ng = N >> 2;                                               // float4 groups per vector
+    const int nb = (ng + 4 * kGatherThreads - 1) / (4 * kGatherThreads); // batches of 4 groups per thread per vector
+    const int total = nvec * nb;                                         // <= kGatherBatches
     const int rot = (int)(((long long)ng * blockIdx.x) / gridDim.x);
-    float4 f[kGatherBatches][4];
-#pragma unroll
-    for (int t = 0; t < kGatherBatches; ++t) {
-        if (t < total) {
-            const int v = t / nb, b = t - v * nb;
-            const float4 *src = reinterpret_cast<const float4 *>(vec + (size_t)v * N);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int g = ctid + kTokConsumers * (4 * b + k);
-                int gg = g + rot;
-                if (gg >= ng) gg -= ng;
-                f[t][k] = g < ng ? __ldcg(src + gg) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-        }
-    }
-    trace_stamp2(trace, scal, ctid); // loads issued
+    const int vt = ctid - 32;
     if (ctid < 32) { // warp 0 combines the per-CTA partials (grid <= 160: five records per lane)
         double pm[3][kRedMax / 32], ps[3][kRedMax / 32];
 #pragma unroll
@@ -437,6 +566,7 @@ __device__ __noinline__ void gather_quantise(uint8_t *planes, double *scal, cons
                 pm[v][t] = on ? __ldcg(vpart + (v * 2 + 0) * kMaxGrid + i) : 0.0;
                 ps[v][t] = on ? __ldcg(vpart + (v * 2 + 1) * kMaxGrid + i) : 0.0;
             }
+        trace_stamp2(trace, scal, ctid); // loads issued
         double m[3] = {0.0, 0.0, 0.0}, s[3] = {0.0, 0.0, 0.0};
 #pragma unroll
         for (int v = 0; v < 3; ++v) {
@@ -455,9 +585,28 @@ __device__ __noinline__ void gather_quantise(uint8_t *planes, double *scal, cons
             scal[3 + ctid] = ss;
             reinterpret_cast<float *>(scal + 6)[ctid] = mm > 0.0 ? (float)((double)kQMaxTok / mm) : 0.0f;
         }
+        tok_sync();
+        trace_stamp2(trace, scal, ctid); // scales known
+        trace_stamp2(trace, scal, ctid); // (warp 0 does not quantise)
+        tok_sync();
+        return;
+    }
+    float4 f[kGatherBatches][4];
+#pragma unroll
+    for (int t = 0; t < kGatherBatches; ++t) {
+        if (t < total) {
+            const int v = t / nb, b = t - v * nb;
+            const float4 *src = reinterpret_cast<const float4 *>(vec + (size_t)v * N);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int g = vt + kGatherThreads * (4 * b + k);
+                int gg = g + rot;
+                if (gg >= ng) gg -= ng;
+                f[t][k] = g < ng ? __ldcg(src + gg) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
     }
     tok_sync();
-    trace_stamp2(trace, scal, ctid); // scales known
     float inv[3];
 #pragma unroll
     for (int v = 0; v < 3; ++v) inv[v] = reinterpret_cast<const float *>(scal + 6)[v];
@@ -469,19 +618,17 @@ __device__ __noinline__ void gather_quantise(uint8_t *planes, double *scal, cons
             uint8_t *pl = planes + (size_t)v * 3 * N;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const int g = ctid + kTokConsumers * (4 * b + k);
+                const int g = vt + kGatherThreads * (4 * b + k);
                 int gg = g + rot;
                 if (gg >= ng) gg -= ng;
                 if (g < ng) quantize4f(f[t][k], iv, pl, N, 4 * gg);
             }
         }
     }
-    trace_stamp2(trace, scal, ctid); // own quantisation done
     tok_sync();
 }
 
-// CPL: 16-byte chunks per lane of one row segment (E / kRowSplit bytes);
-// FULL: E / kRowSplit == CPL*512, i.e. no lane is ever out of range.
+// CPL: 16-byte chunks per lane of one n_embed-byte row segment; FULL: n_embed == CPL*512.
 template <int CPL, bool FULL>
 __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant__ Params p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -498,11 +645,11 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
     const Slices sl = make_slices(E);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp >= kTokWarps) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kProducerRegs));
-        if (warp == kTokWarps && lane == 0) produce_token(p, sm, sl);
+        if (kProducerThreads == 128) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kProducerRegs));
+        if (lane == 0 && warp - kTokWarps < kProducers) produce_token(p, sm, sl, warp - kTokWarps);
         return;
     }
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kConsumerRegs));
+    if (kProducerThreads == 128) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kConsumerRegs));
     const int ctid = threadIdx.x;
     const int ne = sl.ne, nk = sl.nk;
     const int nwe = (ne + 31) >> 5; // warps that own residual elements
@@ -514,19 +661,25 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
     auto stamp = [&]() { trace_stamp(p.trace, sm, ctid); };
     stamp();
     const bool mine = ctid < ne;      // this thread owns residual element j
-    const int j = sl.e0 + (mine ? ctid : 0);
+    const int j0 = sl.e0 + (mine ? ctid : 0);
+    const int j = j0;
     Ctrl *ctrl = p.ctrl;
     unsigned int target = ctrl->bar_base;
     unsigned long long token = ctrl->token;
     if (p.feed_mode == 1) token = ctrl->next;
     else if (p.feed_mode == 2) token = p.stream[ctrl->pos];
-    const size_t so = (size_t)ctrl->slot * p.L * E; // state slot offset
+    const size_t so0 = (size_t)ctrl->slot * p.L * E; // state slot offset
+    const size_t so = so0;
     unsigned int q = 0;                              // exchange-buffer parity counter (one per barrier)
     RingPos rp{0, 0};
-    const uint32_t c_ring = smem_u32(sm.ring), c_full = smem_u32(sm.full), c_empty = smem_u32(sm.empty);
-    const uint32_t c_planes = smem_u32(sm.planes), c_res = smem_u32(sm.res64);
+    const uint32_t c_ring = opaque(smem_u32(sm.ring)), c_full = opaque(smem_u32(sm.full)),
+                   c_empty = opaque(smem_u32(sm.empty));
+    const uint32_t c_planes = opaque(smem_u32(sm.planes)), c_res = opaque(smem_u32(sm.res64));
+    const uint32_t c_tile = opaque((uint32_t)p.tile_bytes), c_stages = opaque((uint32_t)p.stages);
+    const int c_warp = opaque(warp), c_lane = opaque(lane);
+    unsigned long long *const c_ptrace = reinterpret_cast<unsigned long long *>(opaque((size_t)p.ptrace));
     int *const c_tcnt = reinterpret_cast<int *>(sm.scal + 9);
-    // exact integer total of row `i` of a sub whose partials start at `off` (nseg segments per row)
+    // exact integer total of row `i` of the sub whose partials start at res64[off] (nseg per row)
     auto row_total = [&](int off, int i, int nseg) {
         long long t = 0;
         for (int sgm = 0; sgm < nseg; ++sgm) t += sm.res64[off + i * nseg + sgm];
@@ -579,8 +732,9 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
     // parameters of the first LN1 / token-shift slice computation
     double lw = 0, lb = 0, mk = 0, mv = 0, mr = 0, st = 0;
     float rk = 0, rv = 0, rr = 0, ok = 0, ov = 0, orr = 0;
-    auto prefetch_att = [&](int l) {
-        if (mine) {
+    auto prefetch_att = [&](int l, int j, size_t so) {
+        {   // unconditional (j is clamped to an owned element): a guarded assignment would keep the old
+            // values live through the whole layer and push them into local memory
             const size_t lo = (size_t)l * E + j;
             lw = p.ln[(size_t)(4 * l + 2) * E + j];
             lb = p.ln[(size_t)(4 * l + 3) * E + j];
@@ -590,14 +744,17 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
             st = p.sxy[so + lo];
         }
     };
-    if (p.L_run > 0) prefetch_att(0);
+    if (p.L_run > 0) prefetch_att(0, j0, so0);
     stamp();
     grid_sync(p.gbar, target, ctid);
     stamp();
     ++q;
 
     for (int l = 0; l < p.L_run; ++l) {
-        const size_t lo = (size_t)l * E;
+        const int j = opaque(j0);
+        const size_t so = opaque(so0);
+        const int lq = opaque(l);
+        const size_t lo = (size_t)lq * E;
         // ======== LN1 + token shift for the own slice (rwkv.cu:535-540) ==========================
         {
             double xmean = 0.0, x2 = 1.0;
@@ -629,6 +786,7 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
         gather_quantise(sm.planes, sm.scal, vecp(q - 1), vpartp(q - 1), 3, E, ctid, p.trace);
         stamp();
         {
+#ifndef RK_EXP1
             double aa = 0, bb = 0, wd = 0, ub = 0, ewd = 0;
             float ro = 0, oco = 0;
             if (mine) {
@@ -640,18 +798,32 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
                 ro = p.ro[lo + j];
                 oco = p.oco[lo + j];
             }
-            const size_t mo = (size_t)l * E * E;
+#endif
+            const size_t mo = (size_t)lq * E * E;
             (void)mo;
-            rp = consume_sub<CPL, FULL, kRowSplit>(c_ring, c_full, c_empty, (uint32_t)p.tile_bytes, (uint32_t)p.stages, c_planes + (uint32_t)(0), c_res + (uint32_t)(0) * 8u, E, sl.e0, sl.e1, rp, warp, lane, p.ptrace, c_tcnt);
-            rp = consume_sub<CPL, FULL, kRowSplit>(c_ring, c_full, c_empty, (uint32_t)p.tile_bytes, (uint32_t)p.stages, c_planes + (uint32_t)(3 * E), c_res + (uint32_t)(ne * kRowSplit) * 8u, E, sl.e0, sl.e1, rp, warp, lane, p.ptrace, c_tcnt);
-            rp = consume_sub<CPL, FULL, kRowSplit>(c_ring, c_full, c_empty, (uint32_t)p.tile_bytes, (uint32_t)p.stages, c_planes + (uint32_t)(6 * E), c_res + (uint32_t)(2 * ne * kRowSplit) * 8u, E, sl.e0, sl.e1, rp, warp, lane, p.ptrace, c_tcnt);
+            rp = consume_sub<CPL, FULL, 1>(c_ring, c_full, c_empty, c_tile, c_stages, c_planes + (uint32_t)(0), c_res + (uint32_t)(0) * 8u, E, sl.e1 - sl.e0, rp, c_warp, c_lane, c_ptrace, c_tcnt);
+            rp = consume_sub<CPL, FULL, 1>(c_ring, c_full, c_empty, c_tile, c_stages, c_planes + (uint32_t)(3 * E), c_res + (uint32_t)(ne * 1) * 8u, E, sl.e1 - sl.e0, rp, c_warp, c_lane, c_ptrace, c_tcnt);
+            rp = consume_sub<CPL, FULL, 1>(c_ring, c_full, c_empty, c_tile, c_stages, c_planes + (uint32_t)(6 * E), c_res + (uint32_t)(2 * ne * 1) * 8u, E, sl.e1 - sl.e0, rp, c_warp, c_lane, c_ptrace, c_tcnt);
+#ifdef RK_EXP1
+            double aa = 0, bb = 0, wd = 0, ub = 0, ewd = 0;
+            float ro = 0, oco = 0;
+            if (mine) {
+                aa = p.saa[so + lo + j];
+                bb = p.sbb[so + lo + j];
+                wd = p.decay[lo + j];
+                ub = p.bonus[lo + j];
+                ewd = p.expdecay[lo + j];
+                ro = p.ro[lo + j];
+                oco = p.oco[lo + j];
+            }
+#endif
             tok_sync();
             stamp();
             double mx[3] = {0, 0, 0}, of[3] = {0, 0, 0};
             if (mine) {
-                const float kf = (float)(sm.scal[0] * row_total(0, ctid, kRowSplit) + sm.scal[3]);
-                const float vf = (float)(sm.scal[1] * row_total(ne * kRowSplit, ctid, kRowSplit) + sm.scal[4]);
-                const float rf = (float)(sm.scal[2] * row_total(2 * ne * kRowSplit, ctid, kRowSplit) + sm.scal[5]);
+                const float kf = (float)(sm.scal[0] * row_total(0, ctid, 1) + sm.scal[3]);
+                const float vf = (float)(sm.scal[1] * row_total(ne * 1, ctid, 1) + sm.scal[4]);
+                const float rf = (float)(sm.scal[2] * row_total(2 * ne * 1, ctid, 1) + sm.scal[5]);
                 const double vv = (double)vf;
                 const double e1 = exp(ub + wd + (double)kf);
                 double y = (aa + e1 * vv) / (bb + e1);
@@ -678,18 +850,18 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
         double flw = 0, flb = 0, fmk = 0, fmr = 0, fst = 0;
         float frr = 0, frk = 0, forr = 0, fok = 0;
         if (mine) {
-            flw = p.ln[(size_t)(4 * (l + 1)) * E + j];
-            flb = p.ln[(size_t)(4 * (l + 1) + 1) * E + j];
+            flw = p.ln[(size_t)(4 * (lq + 1)) * E + j];
+            flb = p.ln[(size_t)(4 * (lq + 1) + 1) * E + j];
             fmk = p.fmixk[lo + j]; fmr = p.fmixr[lo + j];
             frr = p.rfr[lo + j]; frk = p.rfk[lo + j];
             forr = p.ocfr[lo + j]; fok = p.ocfk[lo + j];
             fst = p.sdd[so + lo + j];
         }
-        rp = consume_sub<CPL, FULL, kRowSplit>(c_ring, c_full, c_empty, (uint32_t)p.tile_bytes, (uint32_t)p.stages, c_planes + (uint32_t)(0), c_res + (uint32_t)(0) * 8u, E, sl.e0, sl.e1, rp, warp, lane, p.ptrace, c_tcnt);
+        rp = consume_sub<CPL, FULL, 1>(c_ring, c_full, c_empty, c_tile, c_stages, c_planes + (uint32_t)(0), c_res + (uint32_t)(0) * 8u, E, sl.e1 - sl.e0, rp, c_warp, c_lane, c_ptrace, c_tcnt);
         tok_sync();
         stamp();
         if (mine) {
-            const float y = (float)(sm.scal[0] * row_total(0, ctid, kRowSplit) + sm.scal[3]);
+            const float y = (float)(sm.scal[0] * row_total(0, ctid, 1) + sm.scal[3]);
             const float xf = (float)sm.xown[ctid] + y;
             sm.xown[ctid] = (double)xf;
         }
@@ -727,7 +899,7 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
         stamp();
         {
             float rvk[2] = {0, 0}, ovk[2] = {0, 0}; // ffn-V scale / offset of the own K rows (<= 2 per thread)
-            const float *rvp = p.rfv + (size_t)l * 4 * E, *ovp = p.ocfv + (size_t)l * 4 * E;
+            const float *rvp = p.rfv + (size_t)lq * 4 * E, *ovp = p.ocfv + (size_t)lq * 4 * E;
 #pragma unroll
             for (int t = 0; t < 2; ++t) {
                 const int i = ctid + t * kTokConsumers;
@@ -736,12 +908,12 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
                     ovk[t] = ovp[sl.k0 + i];
                 }
             }
-            rp = consume_sub<CPL, FULL, kRowSplit>(c_ring, c_full, c_empty, (uint32_t)p.tile_bytes, (uint32_t)p.stages, c_planes + (uint32_t)(0), c_res + (uint32_t)(0) * 8u, E, sl.e0, sl.e1, rp, warp, lane, p.ptrace, c_tcnt);
-            rp = consume_sub<CPL, FULL, kRowSplit>(c_ring, c_full, c_empty, (uint32_t)p.tile_bytes, (uint32_t)p.stages, c_planes + (uint32_t)(3 * E), c_res + (uint32_t)(ne * kRowSplit) * 8u, E, sl.k0, sl.k1, rp, warp, lane, p.ptrace, c_tcnt);
+            rp = consume_sub<CPL, FULL, 1>(c_ring, c_full, c_empty, c_tile, c_stages, c_planes + (uint32_t)(0), c_res + (uint32_t)(0) * 8u, E, sl.e1 - sl.e0, rp, c_warp, c_lane, c_ptrace, c_tcnt);
+            rp = consume_sub<CPL, FULL, 1>(c_ring, c_full, c_empty, c_tile, c_stages, c_planes + (uint32_t)(3 * E), c_res + (uint32_t)(ne * 1) * 8u, E, sl.k1 - sl.k0, rp, c_warp, c_lane, c_ptrace, c_tcnt);
             tok_sync();
             stamp();
             if (mine) {
-                const float y = (float)(sm.scal[0] * row_total(0, ctid, kRowSplit) + sm.scal[3]);
+                const float y = (float)(sm.scal[0] * row_total(0, ctid, 1) + sm.scal[3]);
                 sm.srown[ctid] = (float)(1.0 / (1.0 + exp(-(double)y)));
             }
             double mx[3] = {0, 0, 0}, of[3] = {0, 0, 0};
@@ -750,7 +922,7 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
             for (int t = 0; t < 2; ++t) {
                 const int i = ctid + t * kTokConsumers;
                 if (i < nk) {
-                    float a = (float)(sm.scal[1] * row_total(ne * kRowSplit, i, kRowSplit) + sm.scal[4]);
+                    float a = (float)(sm.scal[1] * row_total(ne * 1, i, 1) + sm.scal[4]);
                     a = a > 0.0f ? a : 0.0f;
                     a = a * a;
                     const float xv = (float)((double)a * (double)rvk[t]);
@@ -768,12 +940,13 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
         // ======== ffn V (rows of 4E bytes, four warps per row) + residual (rwkv.cu:574-577) =========
         gather_quantise(sm.planes, sm.scal, vecp(q - 1), vpartp(q - 1), 1, 4 * E, ctid, p.trace);
         stamp();
-        if (l + 1 < p.L_run) prefetch_att(l + 1);
-        rp = consume_sub<CPL, FULL, 4 * kRowSplit>(c_ring, c_full, c_empty, (uint32_t)p.tile_bytes, (uint32_t)p.stages, c_planes + (uint32_t)(0), c_res + (uint32_t)(0) * 8u, 4 * E, sl.e0, sl.e1, rp, warp, lane, p.ptrace, c_tcnt);
+        rp = consume_sub<CPL, FULL, 4>(c_ring, c_full, c_empty, c_tile, c_stages, c_planes + (uint32_t)(0), c_res + (uint32_t)(0) * 8u, 4 * E, sl.e1 - sl.e0, rp, c_warp, c_lane, c_ptrace, c_tcnt);
+        // issued after the register-hungry core; the loads land during the epilogue + grid barrier
+        if (l + 1 < p.L_run) prefetch_att(lq + 1, j, so);
         tok_sync();
         stamp();
         if (mine) {
-            const float kv = (float)(sm.scal[0] * row_total(0, ctid, 4 * kRowSplit) + sm.scal[3]);
+            const float kv = (float)(sm.scal[0] * row_total(0, ctid, 4 * 1) + sm.scal[3]);
             sm.xown[ctid] = sm.xown[ctid] + (double)(kv * sm.srown[ctid]);
         }
         publish_stats(sm, statp(q), ne, rd, ctid);
@@ -805,14 +978,14 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
     ++q;
     gather_quantise(sm.planes, sm.scal, vecp(q - 1), vpartp(q - 1), 1, E, ctid, p.trace);
     stamp();
-    rp = consume_sub<CPL, FULL, kRowSplit>(c_ring, c_full, c_empty, (uint32_t)p.tile_bytes, (uint32_t)p.stages, c_planes + (uint32_t)(0), c_res + (uint32_t)(0) * 8u, E, sl.v0, sl.v1, rp, warp, lane, p.ptrace, c_tcnt);
+    rp = consume_sub<CPL, FULL, 1>(c_ring, c_full, c_empty, c_tile, c_stages, c_planes + (uint32_t)(0), c_res + (uint32_t)(0) * 8u, E, sl.v1 - sl.v0, rp, c_warp, c_lane, c_ptrace, c_tcnt);
     tok_sync();
     stamp();
     {
         float best = -INFINITY;
         int bidx = 0x7fffffff;
         for (int i = ctid; i < sl.nv; i += kTokConsumers) {
-            const float y = (float)(sm.scal[0] * row_total(0, i, kRowSplit) + sm.scal[3]);
+            const float y = (float)(sm.scal[0] * row_total(0, i, 1) + sm.scal[3]);
             p.logits[sl.v0 + i] = y;
             if (y > best) { // i ascending per thread: first maximum kept
                 best = y;

@@ -20,7 +20,8 @@ class EngineError(RuntimeError):
 
 
 def lib_path():
-    return os.path.join(_PKG, "librwkv_b200.so")
+    # RWKV_B200_LIB: A/B-test another build of the same ABI (tools/sweep.py); default is the in-tree library
+    return os.environ.get("RWKV_B200_LIB") or os.path.join(_PKG, "librwkv_b200.so")
 
 
 def load_library():
@@ -170,11 +171,11 @@ class Engine:
 
     def read_tile_trace(self, grid=148, per_cta=4096):
         """[2][grid][per_cta] globaltimer: tile copy issued by the producer / tile seen ready by consumer thread 0."""
-        a = np.zeros(2 * grid * per_cta, np.uint64)
+        a = np.zeros(3 * grid * per_cta, np.uint64)
         got = self.lib.rwkv_b200_debug_read(self.h, b"ptrace", a.ctypes.data_as(ctypes.c_void_p), a.nbytes)
         if got != a.size:
             raise EngineError("read_tile_trace failed")
-        return a.reshape(2, grid, per_cta)
+        return a.reshape(3, grid, per_cta)
 
     def decode_timed(self, tokens, teacher_forced=True):
         toks = np.ascontiguousarray(np.asarray(tokens, dtype=np.uint64))

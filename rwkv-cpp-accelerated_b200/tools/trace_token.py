@@ -54,23 +54,18 @@ print("barrier release latency after LAST arrival (us): mean %.2f median %.2f" %
 
 # ---- tile-level: how far ahead of the consumers does the producer run? -------------------------
 tt = eng.read_tile_trace().astype(np.int64)
-issue, ready = tt[0, 0], tt[1, 0]  # CTA 0
-n_t = int((issue > 0).sum())
-issue, ready = (issue[:n_t] - t0) / 1e3, (ready[:n_t] - t0) / 1e3
-print("tiles per CTA:", n_t)
-lead = ready - issue
-print("issue->ready latency (us): median %.2f p10 %.2f p90 %.2f" % (np.median(lead), np.percentile(lead, 10), np.percentile(lead, 90)))
-# tiles issued but not yet consumed at each phase start (after each barrier stamp of CTA 0)
-bar_times = [tr[0, i + 1] / 1e3 for i, nm in enumerate(names[:d.shape[1]]) if nm.endswith(".bar")]
-ahead = [int((issue <= bt).sum() - (ready <= bt).sum()) for bt in bar_times[:60]]
-print("tiles in flight/resident at barrier exits (first 60):", ahead)
-k = 200
-print("sample tiles %d..%d: issue" % (k, k + 12), np.round(issue[k:k + 12], 1), "ready", np.round(ready[k:k + 12], 1))
-
-# full tile timeline of layer 2 (7B: 81 tiles per layer: K6 V6 R6 out6 ffnR6 ffnK23 ffnV28)
-per_layer = (n_t - 0) // (L + 1) if L else n_t
-base = 2 * 81
-print("layer-2 tiles: idx issue ready (us)")
-for i in range(base, min(base + 81, n_t)):
-    print("%4d %9.2f %9.2f  lag %.2f" % (i - base, issue[i], ready[i], ready[i] - issue[i]))
+n_cta = 148
+for cta in (0, 77):
+    issue, ready, cyc = tt[0, cta], tt[1, cta], tt[2, cta]
+    n_t = int((issue > 0).sum())
+    issue, ready = (issue[:n_t] - t0) / 1e3, (ready[:n_t] - t0) / 1e3
+    wait = (cyc[:n_t] >> 40).astype(np.float64)
+    clk = (cyc[:n_t] & ((1 << 40) - 1)).astype(np.float64)
+    print("CTA %d: tiles %d; warp-0 wait cycles total %.0f of %.0f token cycles" % (cta, n_t, wait.sum(), clk[-1] - clk[0]))
+    per_layer = 48 if workload == "7b" else None
+    if per_layer:
+        base = 2 * per_layer
+        print("layer-2 tiles of CTA %d: idx issue(us) got(us) lead(us) wait(cyc) dclk(cyc since previous tile)" % cta)
+        for i in range(base, min(base + per_layer, n_t)):
+            print("%4d %9.2f %9.2f %7.2f %7.0f %7.0f" % (i - base, issue[i], ready[i], ready[i] - issue[i], wait[i], clk[i] - clk[i - 1]))
 print("layer-2 stamps (CTA 0, us):", np.round(tr[0, 3 + 2 * 32:3 + 3 * 32] / 1e3, 2))

@@ -17,6 +17,14 @@ REL_TOL = 1e-3
 SEED_TOKEN = 4118  # "###", first token of the storygen prompt
 
 
+def make_engine(pkg, path, mode="token", **kw):
+    """One weight layout serves both execution modes: 'token' = the persistent one-launch-per-token
+    kernel (default), 'staged' = one kernel per phase under a CUDA graph."""
+    eng = pkg.Engine(path, **kw)
+    eng.set_option("mode", mode)
+    return eng
+
+
 def rel_err(got, ref):
     return float(np.abs(got.astype(np.float64) - ref.astype(np.float64)).max() / max(np.abs(ref).max(), 1e-6))
 
@@ -28,8 +36,7 @@ def margin(ref):
 
 def run_pair(pkg, path, steps, threads=None, mode="token"):
     from oracle.oracle import Oracle
-    eng = pkg.Engine(path)
-    eng.set_option("mode", mode)
+    eng = make_engine(pkg, path, mode)
     orc = Oracle(path, threads=threads)
     tok, worst, checked_argmax = SEED_TOKEN, 0.0, 0
     for step in range(steps):
@@ -77,9 +84,7 @@ def test_169m_storygen_length(pkg, make_model):
 def test_graph_and_eager_agree_bitwise(pkg, make_model):
     """The CUDA-graph replay and launch-by-launch execution must be the same computation."""
     path = make_model(2, 2048)
-    a, b = pkg.Engine(path), pkg.Engine(path)
-    a.set_option("mode", "staged")
-    b.set_option("mode", "staged")
+    a, b = make_engine(pkg, path, "staged"), make_engine(pkg, path, "staged")
     b.set_option("graph", 0)
     tok = SEED_TOKEN
     for _ in range(4):
@@ -109,8 +114,7 @@ def test_deterministic_across_runs(pkg, make_model):
 @pytest.mark.parametrize("mode", ["token", "staged"])
 def test_forward_greedy_matches_host_argmax(pkg, make_model, mode):
     path = make_model(2, 2048)
-    e = pkg.Engine(path)
-    e.set_option("mode", mode)
+    e = make_engine(pkg, path, mode)
     tok = SEED_TOKEN
     for _ in range(6):
         nxt, lg = e.forward_greedy(tok, want_logits=True)
@@ -123,8 +127,7 @@ def test_token_and_staged_modes_agree(pkg, make_model):
     """Same arithmetic per element; only the order of the (exact-in-double) partial sums of the
     layernorm statistics differs, so the two engines agree to ~1e-6."""
     path = make_model(3, 768)
-    a, b = pkg.Engine(path), pkg.Engine(path)
-    b.set_option("mode", "staged")
+    a, b = make_engine(pkg, path, "token"), make_engine(pkg, path, "staged")
     tok = SEED_TOKEN
     for _ in range(6):
         la, lb = a.forward([tok])[0], b.forward([tok])[0]
