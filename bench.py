@@ -173,6 +173,20 @@ def run_reference(args, pkg, workload):
     print(json.dumps(base))
 
 
+def ncu_traffic(kernel, workload):
+    """DRAM bytes (read + write) per launch of the dominant kernel, from the committed `ncu --set full`
+    capture of the same command (profiles/r01d_token_traffic.json); null if there is none for this case."""
+    p = os.path.join(ROOT, "profiles", "r01d_token_traffic.json")
+    try:
+        with open(p) as f:
+            t = json.load(f)
+        if kernel == "token" and t.get("workload") == workload:
+            return int(t["dram_bytes_read"]) + int(t["dram_bytes_write"])
+    except (OSError, ValueError, KeyError):
+        pass
+    return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -284,7 +298,7 @@ def main():
                          "gbs": round(v["bytes_per_launch"] / dur_ms / 1e6, 1), "share": round(v["ms_sum"] / total_ms, 4)}
     dom = max(kernels, key=lambda k: kernels[k]["share"])
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s",
-                "frac": round(kernels[dom]["gbs"] / peak, 4), "traffic": None, "peak_source": peak_src,
+                "frac": round(kernels[dom]["gbs"] / peak, 4), "traffic": ncu_traffic(dom, workload), "peak_source": peak_src,
                 "how": "algorithmic bytes per launch / mean CUDA-event duration per launch (eager profile run, %d tokens)" % len(prof_tokens)}
     abytes = algorithmic_bytes_per_token(L, E)
     cb = None
@@ -297,7 +311,7 @@ def main():
         else "tokens/sec single-stream decode RWKV-4 %s uint8; achieved HBM GB/s vs peak" % workload,
         "value": round(value, 2), "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms / args.steps, 5), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u8 weights x 21-bit fixed-point activations (3 int8 limbs, exact int32 accumulate), f64 elementwise",
+        "dtype": "u8 weights x 23-bit fixed-point activations (byte limbs u8,u8,s8; exact int32 dp4a accumulate), f64 elementwise",
         "data": "synthetic",
         "config": {"workload": "RWKV-4 %s shape (L=%d, E=%d, V=50277) uint8, random-init reference-format .bin, greedy single-stream decode, batch 1" % (workload, L, E),
                    "l2": "inputs larger than L2: %.2f GB of weights per token vs 126 MB L2" % (abytes / 1e9),

@@ -26,19 +26,10 @@
 namespace rk {
 
 // ---- thread layout of the token kernel -------------------------------------------------------
-// Four consumer warpgroups (16 warps) + one producer warpgroup (warp 16 streams weights; its
-// other three warps only donate registers). Every weight row is cut into 1 segments
-// handled by different warps, so a lane holds the limbs of only E/2 inputs: registers per thread
-// halve versus one-warp-per-row, which is what makes four warps per scheduler possible; that
-// occupancy is needed to hide LDS / IDP / REDUX latency in the GEMV core and to run the
-// phase-boundary code at a reasonable IPC. setmaxnreg moves the producer warpgroup's registers
-// to the consumers (40 vs 104; the compile-time budget of a 640-thread CTA is 96).
-#ifndef RK_PIPE
-#define RK_PIPE 0
-#endif
-#ifndef RK_PIN
-#define RK_PIN 0
-#endif
+// Eight consumer warps (two per scheduler, each holding the limbs of one n_embed-byte row segment
+// in registers) + one producer warpgroup: its first lane streams the weights, the rest of it only
+// donates registers through setmaxnreg. RK_TOK_WARPS=16 (two warps per row segment, 104
+// registers) is kept compilable for experiments; it measured slower (spills).
 #ifndef RK_CORE_INLINE
 #define RK_CORE_INLINE __forceinline__
 #endif
@@ -86,13 +77,6 @@ __device__ __forceinline__ uint32_t opaque(uint32_t v) {
 __device__ __forceinline__ size_t opaque(size_t v) {
     asm volatile("" : "+l"(v));
     return v;
-}
-
-// two 16-byte shared loads 512 bytes apart in one asm block (keeps them adjacent in the schedule)
-__device__ __forceinline__ void lds128x2(uint32_t addr, uint4 &a, uint4 &b) {
-    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%8];\n\tld.shared.v4.u32 {%4,%5,%6,%7}, [%8+512];"
-                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
-                 : "r"(addr));
 }
 
 // weights (signed bytes) x activation digits (unsigned bytes)
@@ -215,11 +199,6 @@ __device__ __forceinline__ void produce_sub(const Params &p, const Smem &sm, con
     }
 }
 
-// Consumer side of one streamed sub-matrix. All arguments are plain values in registers (a
-// noinline function that takes the Smem struct by reference re-reads its fields from LOCAL memory,
-// and with 227 KB of shared memory carved out there is no L1 to catch that).
-// NSEG = N / E (1 or 4). planes: shared address of limb plane 0 of this sub's activation vector
-// (planes 1, 2 at +N, +2N); res: shared address of this sub's int64 [row][NSEG] partial totals.
 // Half of a unit's weight bytes -> registers: chunks [HALF*H, HALF*H + H) of the lane.
 template <int H, int HALF, bool FULL>
 __device__ __forceinline__ void load_half(uint4 (&w)[H], uint32_t row, int lane, int nchunks) {
@@ -252,15 +231,16 @@ __device__ __forceinline__ void dot_half(const uint4 (&w)[H], const uint4 (&a0)[
     }
 }
 
-// Consumer side of one streamed sub-matrix, software-pipelined in half-units: while a warp runs
-// the dot products of one half of its row segment, the shared-memory loads of the other half -
-// or of the first half of the NEXT tile, which has usually landed already - are in flight.
-// With two warps per scheduler, all eight in step on the same tile, nothing else hides the load
-// phase (32 KB of LDS per tile = 256 clk of shared-memory bandwidth) behind the 384 clk of IDP.4A.
-// The __syncwarp()s pin that order: memory operations may not move across a warp barrier, and
-// ptxas otherwise sinks every load next to its first use (one exposed LDS latency per 16 bytes).
+// Consumer side of one streamed sub-matrix: warp w takes unit w of every tile. All arguments are
+// plain values in registers (the hot loop takes them through opaque(), see above).
 // NSEG = N / E (1 or 4). planes: shared address of limb plane 0 of this sub's activation vector
 // (planes 1, 2 at +N, +2N); res: shared address of this sub's int64 [row][NSEG] partial totals.
+// Variants measured and dropped (gpurun_out A/B of 2026-09-24, 7B shape, tokens/s): this loop 525;
+// all eight loads pinned ahead of the arithmetic with a warp barrier 512; the same as a noinline
+// function 497; software-pipelined in half units (loads of tile t+1 under the arithmetic of tile t,
+// 0.50 instead of 0.64 us per 32 KB tile) as a noinline function 430 - the faster consumer let the
+// producer put 24 MB of bulk copies in flight at every phase boundary and the latency-critical
+// gather loads queued behind them (gather 2.9 -> 6.9 us); inlined it exceeds the register budget.
 template <int CPL, bool FULL, int NSEG>
 __device__ RK_CORE_INLINE RingPos consume_sub(uint32_t ring, uint32_t full0, uint32_t empty0, uint32_t tile_bytes,
                                             uint32_t stages, uint32_t planes, uint32_t res, int N, int nr, RingPos rp,
@@ -274,72 +254,6 @@ __device__ RK_CORE_INLINE RingPos consume_sub(uint32_t ring, uint32_t full0, uin
     const uint32_t unit_off = (uint32_t)(rl * N + seg * seg_len + lane * 16);
     const int ntiles = (nr + TR - 1) / TR;
     if (ntiles <= 0) return rp;
-#if RK_PIPE
-    uint4 h0[H], h1[H];
-    mbar_wait(full0 + 8 * rp.stage, rp.phase);
-    if (rl < nr) load_half<H, 0, FULL>(h0, ring + rp.stage * tile_bytes + unit_off, lane, nchunks);
-    uint4 a0[CPL], a1[CPL], a2[CPL];
-    {
-        const uint32_t pl = planes + (uint32_t)(seg * seg_len);
-#pragma unroll
-        for (int i = 0; i < CPL; ++i) {
-            const int c = lane + 32 * i;
-            if (FULL || c < nchunks) {
-                a0[i] = lds128(pl + c * 16);
-                a1[i] = lds128(pl + N + c * 16);
-                a2[i] = lds128(pl + 2 * N + c * 16);
-            } else {
-                a0[i] = a1[i] = a2[i] = make_uint4(0, 0, 0, 0);
-            }
-        }
-    }
-    uint32_t dst = res + (uint32_t)((rl * NSEG + seg) * 8);
-    int row = rl; // this warp's row (relative to the sub) in the current tile
-    for (int t = 0; t < ntiles; ++t) {
-        const bool mine = row < nr, have_next = t + 1 < ntiles;
-        RingPos nx = rp;
-        nx.advance(stages);
-        if (mine) load_half<H, 1, FULL>(h1, ring + rp.stage * tile_bytes + unit_off, lane, nchunks);
-        __syncwarp();
-        if (ptrace != nullptr && threadIdx.x == 0) { // trace row [1]: %globaltimer when warp 0 starts on the tile
-            const int c = *tile_cnt;
-            if (c < kTileTraceMax) {
-                unsigned long long tm;
-                asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tm));
-                ptrace[((size_t)gridDim.x + blockIdx.x) * kTileTraceMax + c] = tm;
-            }
-            *tile_cnt = c + 1;
-        }
-        int acc[6] = {0, 0, 0, 0, 0, 0};
-        if (mine) dot_half<CPL, H, 0>(h0, a0, a1, a2, acc);
-        // one poll: if the next tile has landed, start on it before the second half's arithmetic
-        bool pre = false;
-        if (have_next) {
-            pre = __all_sync(0xffffffffu, mbar_try_wait(full0 + 8 * nx.stage, nx.phase));
-            if (pre && row + TR < nr) load_half<H, 0, FULL>(h0, ring + nx.stage * tile_bytes + unit_off, lane, nchunks);
-        }
-        __syncwarp();
-        if (mine) {
-            dot_half<CPL, H, 1>(h1, a0, a1, a2, acc);
-            const int t0 = __reduce_add_sync(0xffffffffu, acc[0] + acc[1]);
-            const int t1 = __reduce_add_sync(0xffffffffu, acc[2] + acc[3]);
-            const int t2 = __reduce_add_sync(0xffffffffu, acc[4] + acc[5]);
-            if (lane == 0) {
-                const long long tot = (((long long)t2 << 8) + (long long)t1) * 256 + (long long)t0;
-                asm volatile("st.shared.u64 [%0], %1;" ::"r"(dst), "l"(tot) : "memory");
-            }
-        }
-        dst += 8 * 8; // eight units per tile
-        __syncwarp();
-        if (lane == 0) mbar_arrive(empty0 + 8 * rp.stage);
-        if (have_next && !pre) {
-            mbar_wait(full0 + 8 * nx.stage, nx.phase);
-            if (row + TR < nr) load_half<H, 0, FULL>(h0, ring + nx.stage * tile_bytes + unit_off, lane, nchunks);
-        }
-        row += TR;
-        rp = nx;
-    }
-#else
     uint4 a0[CPL], a1[CPL], a2[CPL];
     {
         const uint32_t pl = planes + (uint32_t)(seg * seg_len);
@@ -373,9 +287,6 @@ __device__ RK_CORE_INLINE RingPos consume_sub(uint32_t ring, uint32_t full0, uin
             uint4 h0[H], h1[H];
             load_half<H, 0, FULL>(h0, wrow, lane, nchunks);
             load_half<H, 1, FULL>(h1, wrow, lane, nchunks);
-#if RK_PIN
-            __syncwarp();
-#endif
             int acc[6] = {0, 0, 0, 0, 0, 0};
             dot_half<CPL, H, 0>(h0, a0, a1, a2, acc);
             dot_half<CPL, H, 1>(h1, a0, a1, a2, acc);
@@ -393,8 +304,6 @@ __device__ RK_CORE_INLINE RingPos consume_sub(uint32_t ring, uint32_t full0, uin
         if (lane == 0) mbar_arrive(empty0 + 8 * rp.stage);
         rp.advance(stages);
     }
-#endif
-    // leave the ring position after the last tile of this sub
     return rp;
 }
 
