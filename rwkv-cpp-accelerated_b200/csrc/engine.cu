@@ -62,6 +62,9 @@ struct rwkv_b200_model {
     int sms = 0;
     int grid = 0;
     int cpl = 0;
+    size_t xch_bytes = 0;   // exchange block (peer-visible with tensor parallelism)
+    bool tp_wired = false;  // peers' exchange blocks imported
+    std::vector<void *> ipc_opened;
     unsigned long long L = 0, E = 0, max_gpt = 1;
     cudaStream_t stream = nullptr;
     rk::Params p{};
@@ -180,6 +183,8 @@ void configure_mode(M *m) {
 }
 
 int launch_token(M *m, int feed, bool greedy, const unsigned long long *stream, cudaStream_t s) {
+    if (m->tp_size > 1 && !m->tp_wired)
+        return fail(7, "tensor parallelism: call rwkv_b200_tp_import with every rank's handle before the first forward");
     rk::Params prm = m->p;
     prm.L_run = layers_to_run(m);
     prm.feed_mode = feed;
@@ -366,7 +371,7 @@ int do_load(M *m, const char *path, int quiet) {
 
     m->cpl = E <= 1024 ? 2 : E <= 2048 ? 4 : E <= 4096 ? 8 : 10;
     if (const char *e = getenv("RWKV_B200_MODE")) {
-        if (std::string(e) == "staged") m->token_mode = false;
+        if (std::string(e) == "staged" && m->tp_size == 1) m->token_mode = false;
     }
     rk::Params &p = m->p;
     p.L = (int)L;
@@ -461,17 +466,24 @@ int do_load(M *m, const char *path, int quiet) {
     float *b3;
     if ((rc = dmalloc(m, &p.x, E)) || (rc = dmalloc(m, &p.xy_new, E)) || (rc = dmalloc(m, &p.dd_new, E)) ||
         (rc = dmalloc(m, &p.xs_o, E)) || (rc = dmalloc(m, &p.sr, E)) || (rc = dmalloc(m, &p.xs_v, 4 * E)) ||
-        (rc = dmalloc(m, &p.logits, (size_t)binfmt::kVocab)) || (rc = dmalloc(m, &p.part_o, 2 * rk::kMaxGrid)) ||
+        (rc = dmalloc(m, &p.part_o, 2 * rk::kMaxGrid)) ||
         (rc = dmalloc(m, &p.part_v, 2 * rk::kMaxGrid)) || (rc = dmalloc(m, &p.ctrl, 1)) ||
         (rc = dmalloc(m, &b1, E)) || (rc = dmalloc(m, &fkb, E)) || (rc = dmalloc(m, &fvb, E)) ||
         (rc = dmalloc(m, &b3, E)))
         return rc;
     CK(cudaMemsetAsync(p.ctrl, 0, sizeof(rk::Ctrl), m->stream));
-    if ((rc = dmalloc(m, &p.gbar, 64)) || (rc = dmalloc(m, &p.stat_part, 4 * rk::kMaxGrid)) ||
-        (rc = dmalloc(m, &p.vec, 8 * E)) || (rc = dmalloc(m, &p.vpart, 12 * rk::kMaxGrid)) ||
-        (rc = dmalloc(m, &p.amax_val, rk::kMaxGrid)) || (rc = dmalloc(m, &p.amax_idx, rk::kMaxGrid)))
-        return rc;
-    CK(cudaMemsetAsync(p.gbar, 0, 64 * sizeof(unsigned int), m->stream));
+    // exchange block: [0,128) barrier counter | [128,512) accumulators | [1024, +32E) vec | logits
+    {
+        unsigned char *x = nullptr;
+        m->xch_bytes = (1024 + 32 * (size_t)E + 4 * (size_t)binfmt::kVocab + 255) & ~(size_t)255;
+        if ((rc = dmalloc(m, &x, m->xch_bytes))) return rc;
+        CK(cudaMemsetAsync(x, 0, m->xch_bytes, m->stream));
+        for (int g = 0; g < 8; ++g) p.xch[g] = x; // peers are wired by rwkv_b200_tp_import
+        p.gbar = reinterpret_cast<unsigned int *>(x);
+        p.acc = reinterpret_cast<unsigned long long *>(x + 128);
+        p.vec = reinterpret_cast<float *>(x + 1024);
+        p.logits = reinterpret_cast<float *>(x + 1024 + 32 * (size_t)E);
+    }
     {
         int coop = 0;
         CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, m->device));
@@ -520,7 +532,8 @@ int rwkv_b200_load_tp(const char *path, unsigned long long max_gpt, int device, 
                       rwkv_b200_model **out, unsigned long long *n_layers, unsigned long long *n_embed) {
     if (!path || !out) return fail(1, "null argument");
     *out = nullptr;
-    if (tp_size != 1) return fail(7, "tensor-parallel load (tp_size=%d) is not available in this build", tp_size);
+    if (tp_size < 1 || tp_size > 8 || tp_rank < 0 || tp_rank >= tp_size)
+        return fail(7, "tensor parallelism: rank %d of %d is not supported (1..8 ranks)", tp_rank, tp_size);
     if (rwkv_b200_device_count() <= device || device < 0)
         return fail(6, "CUDA device %d not available (no CPU fallback exists)", device);
     M *m = new M;
@@ -551,6 +564,7 @@ void rwkv_b200_free(rwkv_b200_model *m) {
     cudaSetDevice(m->device);
     if (m->stream) cudaStreamSynchronize(m->stream);
     drop_graphs(m);
+    for (void *p : m->ipc_opened) cudaIpcCloseMemHandle(p);
     for (void *p : m->allocs) cudaFree(p);
     if (m->h_ctrl) cudaFreeHost(m->h_ctrl);
     if (m->h_logits) cudaFreeHost(m->h_logits);
@@ -816,6 +830,7 @@ int rwkv_b200_set_option(rwkv_b200_model *m, const char *key, const char *value)
     } else if (k == "mode") {
         const bool want_token = std::string(value) == "token";
         if (!want_token && std::string(value) != "staged") return fail(1, "mode must be 'token' or 'staged'");
+        if (!want_token && m->tp_size > 1) return fail(1, "the staged kernels are single-GPU only");
         m->token_mode = want_token;
         configure_mode(m);
     }
@@ -868,8 +883,36 @@ long long rwkv_b200_debug_read(rwkv_b200_model *m, const char *name, void *dst, 
     return (long long)count;
 }
 
-size_t rwkv_b200_tp_buffer_bytes(const rwkv_b200_model *) { return 0; }
-int rwkv_b200_tp_export(rwkv_b200_model *, void *) { return fail(7, "tensor parallelism not available in this build"); }
-int rwkv_b200_tp_import(rwkv_b200_model *, const void *) { return fail(7, "tensor parallelism not available in this build"); }
+size_t rwkv_b200_tp_buffer_bytes(const rwkv_b200_model *m) { return m ? m->xch_bytes : 0; }
+
+int rwkv_b200_tp_export(rwkv_b200_model *m, void *ipc_handle_64) {
+    if (check_model(m) || !ipc_handle_64) return fail(1, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaSetDevice(m->device);
+    CK(cudaStreamSynchronize(m->stream)); // the block is zero-filled before anybody maps it
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, m->p.xch[m->tp_rank]));
+    memcpy(ipc_handle_64, &h, 64);
+    return 0;
+}
+
+int rwkv_b200_tp_import(rwkv_b200_model *m, const void *ipc_handles) {
+    if (check_model(m) || !ipc_handles) return fail(1, "null argument");
+    if (m->tp_wired) return fail(7, "peer exchange blocks already imported");
+    cudaSetDevice(m->device);
+    const unsigned char *hs = static_cast<const unsigned char *>(ipc_handles);
+    for (int g = 0; g < m->tp_size; ++g) {
+        if (g == m->tp_rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, hs + 64 * (size_t)g, 64);
+        void *ptr = nullptr;
+        CK(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        m->ipc_opened.push_back(ptr);
+        m->p.xch[g] = static_cast<unsigned char *>(ptr);
+    }
+    m->tp_wired = true;
+    drop_graphs(m);
+    return 0;
+}
 
 } // extern "C"

@@ -85,12 +85,12 @@ struct Params {
     int feed_mode;                     // 0: ctrl->token, 1: ctrl->next (free-running), 2: stream[ctrl->pos]
     int greedy;                        // 1: finish with an on-device argmax into ctrl->next
     const unsigned long long *stream;  // device-resident token stream (feed_mode 2)
-    unsigned int *gbar;                // grid barrier counter (monotonic)
-    double *stat_part;                 // [2 parity][2][kMaxGrid]   partial sum(x), sum(x^2) per CTA
-    float *vec;                        // [2 parity][4E]            next-phase activation vector(s), pre-scaled by r
-    double *vpart;                     // [2 parity][3][2][kMaxGrid] per-vector partial max|xs|, sum x*oc per CTA
-    float *amax_val;                   // [kMaxGrid] per-CTA best logit
-    int *amax_idx;                     // [kMaxGrid] and its index
+    // The exchange block of this rank (one allocation, peer-mapped by the other ranks): gbar, acc,
+    // vec and logits all point into xch[tp_rank]; xch[g] is rank g's block as seen from here.
+    unsigned char *xch[8];
+    unsigned int *gbar;                // grid barrier counter (monotonic, counts the CTAs of all ranks)
+    unsigned long long *acc;           // [3 phases][16] integer accumulators (token_kernel.cuh)
+    float *vec;                        // [2 parity][4E] next-phase activation vector(s), pre-scaled by r
     unsigned long long *trace;         // optional [grid][kTraceMax] globaltimer stamps (debug), or nullptr
     unsigned long long *ptrace;        // optional [2][grid][kTileTraceMax]: tile issue / tile ready times (debug)
 };

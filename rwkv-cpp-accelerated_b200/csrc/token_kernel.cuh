@@ -86,26 +86,76 @@ __device__ __forceinline__ int dp4a_su(uint32_t a, uint32_t b, int c) {
     return d;
 }
 
-__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p) {
+// ---- exchange block, peers and scopes -----------------------------------------------------------
+// Everything CTAs exchange lives in ONE allocation per GPU (the "exchange block": barrier counter,
+// accumulators, activation vectors, logits). With tensor parallelism (tp_size ranks, one GPU each)
+// the G GPUs simply form one grid of G*148 CTAs: slices and rows are split over the global CTA
+// index, every publish is stored into the exchange block of EVERY rank (peer-mapped over NVLink,
+// Params::xch[g]), every read is local, and the grid barrier counts the CTAs of all ranks at system
+// scope. tp_size == 1 is the same code with one "peer" (itself) and gpu scope.
+template <class T> __device__ __forceinline__ T *peer_ptr(const Params &p, T *local, int g) {
+    return reinterpret_cast<T *>(p.xch[g] + (reinterpret_cast<unsigned char *>(local) - p.xch[p.tp_rank]));
+}
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *ptr, bool sys) {
     unsigned int v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    if (sys) asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
+    else asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
     return v;
 }
+__device__ __forceinline__ void red_add_u64(unsigned long long *ptr, unsigned long long v, bool sys) {
+    if (sys) asm volatile("red.relaxed.sys.global.add.u64 [%0], %1;" ::"l"(ptr), "l"(v) : "memory");
+    else asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(ptr), "l"(v) : "memory");
+}
+__device__ __forceinline__ void red_max_u64(unsigned long long *ptr, unsigned long long v, bool sys) {
+    if (sys) asm volatile("red.relaxed.sys.global.max.u64 [%0], %1;" ::"l"(ptr), "l"(v) : "memory");
+    else asm volatile("red.relaxed.gpu.global.max.u64 [%0], %1;" ::"l"(ptr), "l"(v) : "memory");
+}
 
-// Grid barrier over the consumer threads of all CTAs (the producer warps do not take part).
-__device__ __forceinline__ void grid_sync(unsigned int *bar, unsigned int &target, int ctid) {
+// Accumulators: the per-CTA partial sums / maxima of a phase are combined with integer atomics into
+// a few 64-bit words per rank instead of being published as per-CTA records (G*148 records would
+// cost every reader several L2 round trips). Integer adds commute, so the result is still
+// bit-deterministic. Sums are fixed point (2^-32; sum x^2: 2^-20), maxima are the bit patterns of
+// non-negative doubles (order-preserving as unsigned integers), the arg-max key packs an
+// order-preserving image of the logit above ~index (largest logit, then smallest index, wins).
+// Three buffers rotate with the phase number: written in phase n, read in phase n+1, cleared in
+// phase n+2 by CTA 0 of the owning rank.
+constexpr int kAccSlots = 16;
+constexpr int kAccS1 = 0, kAccS2 = 1, kAccMax = 2, kAccSum = 5, kAccArg = 8;
+__device__ __forceinline__ unsigned long long fx32(double v) {
+    return (unsigned long long)__double2ll_rn(v * 4294967296.0);
+}
+__device__ __forceinline__ double unfx32(unsigned long long u) { return (double)(long long)u * (1.0 / 4294967296.0); }
+__device__ __forceinline__ unsigned long long fx20(double v) {
+    return (unsigned long long)__double2ll_rn(v * 1048576.0);
+}
+__device__ __forceinline__ double unfx20(unsigned long long u) { return (double)(long long)u * (1.0 / 1048576.0); }
+__device__ __forceinline__ unsigned long long *acc_buf(const Params &p, unsigned int phase) {
+    return p.acc + (size_t)(phase % 3u) * kAccSlots;
+}
+
+// Grid barrier over the consumer threads of all CTAs of all ranks (the producer warps do not take
+// part). Afterwards CTA 0 clears the accumulator buffer that the phase after next will write.
+__device__ __forceinline__ void grid_sync(const Params &p, unsigned int &target, unsigned int &phase, int ctid) {
     tok_sync();
-    target += gridDim.x;
+    const bool sys = p.tp_size > 1;
+    target += gridDim.x * (unsigned int)p.tp_size;
     if (ctid == 0) {
         // release: everything this CTA wrote (ordered before by the bar.sync above) is visible to any
         // thread that observes the increment with an acquire load.
-        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
+        if (sys) {
+            for (int g = 0; g < p.tp_size; ++g)
+                asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(peer_ptr(p, p.gbar, g)) : "memory");
+        } else {
+            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.gbar) : "memory");
+        }
         unsigned int spins = 0;
-        while ((int)(ld_acquire_u32(bar) - target) < 0) {
+        while ((int)(ld_acquire_u32(p.gbar, sys) - target) < 0) {
             if (++spins > (1u << 25)) __trap();
         }
     }
     tok_sync();
+    ++phase;
+    if (blockIdx.x == 0 && ctid < kAccSlots) acc_buf(p, phase + 1)[ctid] = 0ull;
 }
 
 // Reductions in the phase-boundary code. Only a few threads ever hold data there (the <= 64 slice
@@ -313,13 +363,18 @@ struct Slices {
     int k0, k1, nk; // rows of the 4E-row ffn key matrix
     int v0, v1, nv; // rows of the head
 };
-__device__ __forceinline__ Slices make_slices(int E) {
+__device__ __forceinline__ void split_rows_g(int M, int gb, int gn, int &r0, int &r1) {
+    r0 = (int)(((long long)M * gb) / gn);
+    r1 = (int)(((long long)M * (gb + 1)) / gn);
+}
+// gb / gn: index of this CTA in, and size of, the grid formed by all ranks
+__device__ __forceinline__ Slices make_slices(int E, int gb, int gn) {
     Slices s;
-    split_rows(E, s.e0, s.e1);
+    split_rows_g(E, gb, gn, s.e0, s.e1);
     s.ne = s.e1 - s.e0;
-    split_rows(4 * E, s.k0, s.k1);
+    split_rows_g(4 * E, gb, gn, s.k0, s.k1);
     s.nk = s.k1 - s.k0;
-    split_rows(kVocab, s.v0, s.v1);
+    split_rows_g(kVocab, gb, gn, s.v0, s.v1);
     s.nv = s.v1 - s.v0;
     return s;
 }
@@ -343,26 +398,11 @@ __device__ __forceinline__ void produce_token(const Params &p, const Smem &sm, c
     produce_sub(p, sm, p.whead, E, sl.v0, sl.v1, rp, pol, tcount, pw);
 }
 
-// mean / std of the full residual stream from the per-CTA partial sums, with the reference's f32
-// rounding of the two accumulators (rwkv.cu:412-465, 43-44). sum((x-m)^2) = s2 - 2 m s1 + E m^2.
-// Warp-local: every warp that calls it loads the partials itself (no block barrier); only the
-// warps that own residual elements call it.
-__device__ __forceinline__ void stats_from_parts(const Params &p, const double *part, int lane, double &xmean, double &x2) {
-    double a1[kRedMax / 32], a2[kRedMax / 32];
-#pragma unroll
-    for (int t = 0; t < kRedMax / 32; ++t) { // all loads in flight: one L2 round trip
-        const int i = lane + 32 * t;
-        a1[t] = i < (int)gridDim.x ? __ldcg(part + i) : 0.0;
-        a2[t] = i < (int)gridDim.x ? __ldcg(part + kMaxGrid + i) : 0.0;
-    }
-    double s1 = 0.0, s2 = 0.0;
-#pragma unroll
-    for (int t = 0; t < kRedMax / 32; ++t) {
-        s1 += a1[t];
-        s2 += a2[t];
-    }
-    s1 = warp_sum(s1);
-    s2 = warp_sum(s2);
+// mean / std of the full residual stream from the accumulated sum(x), sum(x^2), with the
+// reference's f32 rounding of the two accumulators (rwkv.cu:412-465, 43-44).
+// sum((x-m)^2) = s2 - 2 m s1 + E m^2. Every calling lane loads the two words itself (broadcast).
+__device__ __forceinline__ void stats_from_acc(const Params &p, const unsigned long long *acc, double &xmean, double &x2) {
+    const double s1 = unfx32(__ldcg(acc + kAccS1)), s2 = unfx20(__ldcg(acc + kAccS2));
     const double E = (double)p.E;
     const float mean_acc = (float)s1;
     const double mean_f = (double)(mean_acc / (float)p.E);
@@ -373,8 +413,8 @@ __device__ __forceinline__ void stats_from_parts(const Params &p, const double *
     x2 = (double)sqrtf(var_acc / (float)(p.E - 1));
 }
 
-// Publish this CTA's partial {sum x, sum x^2} of its slice.
-__device__ __forceinline__ void publish_stats(const Smem &sm, double *part, int ne, Red &rd, int ctid) {
+// Accumulate this CTA's {sum x, sum x^2} of its slice on every rank.
+__device__ __forceinline__ void publish_stats(const Params &p, const Smem &sm, unsigned int phase, int ne, Red &rd, int ctid) {
     double s[2] = {0.0, 0.0};
     if (ctid < ne) {
         const double v = sm.xown[ctid];
@@ -382,21 +422,32 @@ __device__ __forceinline__ void publish_stats(const Smem &sm, double *part, int 
         s[1] = v * v;
     }
     owners_reduce<2, 0>(s, nullptr, rd, ctid, ne);
-    if (ctid == 0) {
-        part[blockIdx.x] = s[0];
-        part[kMaxGrid + blockIdx.x] = s[1];
+    if (ctid == 0 && ne > 0) {
+        unsigned long long *acc = acc_buf(p, phase);
+        const bool sys = p.tp_size > 1;
+        for (int g = 0; g < p.tp_size; ++g) {
+            unsigned long long *a = peer_ptr(p, acc, g);
+            red_add_u64(a + kAccS1, fx32(s[0]), sys);
+            red_add_u64(a + kAccS2, fx20(s[1]), sys);
+        }
     }
 }
 
-// Publish per-vector partial {max |xs|, sum x*oc} of this CTA (data in the first `nact` threads).
+// Accumulate per-vector {max |xs|, sum x*oc} of this CTA (data in the first `nact` threads).
 template <int NVEC>
-__device__ __forceinline__ void publish_vparts(double *vpart, double *mx, double *of, Red &rd, int ctid, int nact) {
+__device__ __forceinline__ void publish_vparts(const Params &p, unsigned int phase, double *mx, double *of, Red &rd,
+                                               int ctid, int nact) {
     owners_reduce<NVEC, NVEC>(of, mx, rd, ctid, nact);
-    if (ctid == 0) {
+    if (ctid == 0 && nact > 0) {
+        unsigned long long *acc = acc_buf(p, phase);
+        const bool sys = p.tp_size > 1;
+        for (int g = 0; g < p.tp_size; ++g) {
+            unsigned long long *a = peer_ptr(p, acc, g);
 #pragma unroll
-        for (int v = 0; v < NVEC; ++v) {
-            vpart[(v * 2 + 0) * kMaxGrid + blockIdx.x] = mx[v];
-            vpart[(v * 2 + 1) * kMaxGrid + blockIdx.x] = of[v];
+            for (int v = 0; v < NVEC; ++v) {
+                red_max_u64(a + kAccMax + v, (unsigned long long)__double_as_longlong(mx[v]), sys);
+                red_add_u64(a + kAccSum + v, fx32(of[v]), sys);
+            }
         }
     }
 }
@@ -447,59 +498,19 @@ __device__ __forceinline__ void trace_stamp2(unsigned long long *trace, double *
     }
 }
 
-// After a barrier: fetch every CTA's partials and the `nvec` activation vectors of length N
-// (vector v -> limb planes at offset v*3*N), reduce the partials, then quantise from registers.
-// Warp 0 loads and reduces the per-CTA partials; warps 1.. load the vectors (up to 24 x 16 B per
-// thread) - everything is issued before anything is consumed, so the whole gather costs ONE L2
-// round trip. The two roles keep their loads in disjoint register sets of the same function; when
-// every warp did both, the 96 + 60 registers spilled and each spill store waited for its load
-// (ncu r01d: 6 % of all samples on STL). Every CTA walks the vector from a different starting
-// offset so that the 148 CTAs do not hit the same L2 lines at the same moment.
-constexpr int kGatherBatches = 6;                 // x 4 float4 groups x 224 threads x 4 elements >= 4*5120
-constexpr int kGatherThreads = kTokConsumers - 32; // warps 1..7
-__device__ RK_GATHER_INLINE void gather_quantise(uint8_t *planes, double *scal, const float *vec, const double *vpart,
-                                             int nvec, int N, int ctid, unsigned long long *trace) {
-    const int ng = N >> 2;                                               // float4 groups per vector
-    const int nb = (ng + 4 * kGatherThreads - 1) / (4 * kGatherThreads); // batches of 4 groups per thread per vector
-    const int total = nvec * nb;                                         // <= kGatherBatches
-    const int rot = (int)(((long long)ng * blockIdx.x) / gridDim.x);
-    const int vt = ctid - 32;
-    if (ctid < 32) { // warp 0 combines the per-CTA partials (grid <= 160: five records per lane)
-        double pm[3][kRedMax / 32], ps[3][kRedMax / 32];
-#pragma unroll
-        for (int v = 0; v < 3; ++v)
-#pragma unroll
-            for (int t = 0; t < kRedMax / 32; ++t) { // all loads in flight: one L2 round trip
-                const int i = ctid + 32 * t;
-                const bool on = v < nvec && i < (int)gridDim.x;
-                pm[v][t] = on ? __ldcg(vpart + (v * 2 + 0) * kMaxGrid + i) : 0.0;
-                ps[v][t] = on ? __ldcg(vpart + (v * 2 + 1) * kMaxGrid + i) : 0.0;
-            }
-        trace_stamp2(trace, scal, ctid); // loads issued
-        double m[3] = {0.0, 0.0, 0.0}, s[3] = {0.0, 0.0, 0.0};
-#pragma unroll
-        for (int v = 0; v < 3; ++v) {
-#pragma unroll
-            for (int t = 0; t < kRedMax / 32; ++t) {
-                m[v] = fmax(m[v], pm[v][t]);
-                s[v] += ps[v][t];
-            }
-            m[v] = warp_max(m[v]);
-            s[v] = warp_sum(s[v]);
-        }
-        if (ctid < 3) {
-            const double mm = ctid == 0 ? m[0] : ctid == 1 ? m[1] : m[2];
-            const double ss = ctid == 0 ? s[0] : ctid == 1 ? s[1] : s[2];
-            scal[ctid] = mm / (double)kQMaxTok;
-            scal[3 + ctid] = ss;
-            reinterpret_cast<float *>(scal + 6)[ctid] = mm > 0.0 ? (float)((double)kQMaxTok / mm) : 0.0f;
-        }
-        tok_sync();
-        trace_stamp2(trace, scal, ctid); // scales known
-        trace_stamp2(trace, scal, ctid); // (warp 0 does not quantise)
-        tok_sync();
-        return;
-    }
+// After a barrier: fetch the `nvec` activation vectors of length N (vector v -> limb planes at offset
+// v*3*N) and the accumulated {max |xs|, sum x*oc}, then quantise from registers. All loads (up to
+// 24 x 16 B per thread) are issued before anything is consumed, so the whole gather costs ONE L2
+// round trip; every CTA walks the vector from a different starting offset so that the CTAs do not
+// hit the same L2 lines at the same moment.
+constexpr int kGatherBatches = kTokWarps == 8 ? 6 : 3; // x 4 float4 groups x threads x 4 elements >= 4*5120
+__device__ RK_GATHER_INLINE void gather_quantise(uint8_t *planes, double *scal, const float *vec,
+                                             const unsigned long long *acc, int nvec, int N, int ctid, int rot_num,
+                                             int rot_den, unsigned long long *trace) {
+    const int ng = N >> 2;                                             // float4 groups per vector
+    const int nb = (ng + 4 * kTokConsumers - 1) / (4 * kTokConsumers); // batches of 4 groups per thread per vector
+    const int total = nvec * nb;                                       // <= kGatherBatches
+    const int rot = (int)(((long long)ng * rot_num) / rot_den);
     float4 f[kGatherBatches][4];
 #pragma unroll
     for (int t = 0; t < kGatherBatches; ++t) {
@@ -508,14 +519,26 @@ __device__ RK_GATHER_INLINE void gather_quantise(uint8_t *planes, double *scal, 
             const float4 *src = reinterpret_cast<const float4 *>(vec + (size_t)v * N);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const int g = vt + kGatherThreads * (4 * b + k);
+                const int g = ctid + kTokConsumers * (4 * b + k);
                 int gg = g + rot;
                 if (gg >= ng) gg -= ng;
                 f[t][k] = g < ng ? __ldcg(src + gg) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
     }
+    if (ctid < 3) {
+        double mm = 0.0, ss = 0.0;
+        if (ctid < nvec) {
+            mm = __longlong_as_double((long long)__ldcg(acc + kAccMax + ctid));
+            ss = unfx32(__ldcg(acc + kAccSum + ctid));
+        }
+        scal[ctid] = mm / (double)kQMaxTok;
+        scal[3 + ctid] = ss;
+        reinterpret_cast<float *>(scal + 6)[ctid] = mm > 0.0 ? (float)((double)kQMaxTok / mm) : 0.0f;
+    }
+    trace_stamp2(trace, scal, ctid); // loads issued
     tok_sync();
+    trace_stamp2(trace, scal, ctid); // scales known
     float inv[3];
 #pragma unroll
     for (int v = 0; v < 3; ++v) inv[v] = reinterpret_cast<const float *>(scal + 6)[v];
@@ -527,13 +550,14 @@ __device__ RK_GATHER_INLINE void gather_quantise(uint8_t *planes, double *scal, 
             uint8_t *pl = planes + (size_t)v * 3 * N;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const int g = vt + kGatherThreads * (4 * b + k);
+                const int g = ctid + kTokConsumers * (4 * b + k);
                 int gg = g + rot;
                 if (gg >= ng) gg -= ng;
                 if (g < ng) quantize4f(f[t][k], iv, pl, N, 4 * gg);
             }
         }
     }
+    trace_stamp2(trace, scal, ctid); // own quantisation done
     tok_sync();
 }
 
@@ -551,7 +575,8 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
     }
     __syncthreads();
     const int E = p.E;
-    const Slices sl = make_slices(E);
+    const int gn = (int)gridDim.x * p.tp_size, gb = p.tp_rank * (int)gridDim.x + (int)blockIdx.x;
+    const Slices sl = make_slices(E, gb, gn);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp >= kTokWarps) {
         if (kProducerThreads == 128) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kProducerRegs));
@@ -580,6 +605,8 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
     const size_t so0 = (size_t)ctrl->slot * p.L * E; // state slot offset
     const size_t so = so0;
     unsigned int q = 0;                              // exchange-buffer parity counter (one per barrier)
+    unsigned int phase = target / (unsigned int)gn;  // global phase number: selects the accumulator buffer
+    const bool sys = p.tp_size > 1;
     RingPos rp{0, 0};
     const uint32_t c_ring = opaque(smem_u32(sm.ring)), c_full = opaque(smem_u32(sm.full)),
                    c_empty = opaque(smem_u32(sm.empty));
@@ -594,9 +621,12 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
         for (int sgm = 0; sgm < nseg; ++sgm) t += sm.res64[off + i * nseg + sgm];
         return (double)t;
     };
-    auto statp = [&](unsigned int qq) { return p.stat_part + (size_t)(qq & 1) * 2 * kMaxGrid; };
     auto vecp = [&](unsigned int qq) { return p.vec + (size_t)(qq & 1) * 4 * E; };
-    auto vpartp = [&](unsigned int qq) { return p.vpart + (size_t)(qq & 1) * 6 * kMaxGrid; };
+    // store one value of a published vector into the exchange block of every rank
+    auto put = [&](float *local, float v) {
+        if (!sys) { *local = v; return; }
+        for (int g = 0; g < p.tp_size; ++g) *peer_ptr(p, local, g) = v;
+    };
 
     // ---- x = LN0(emb[token]) for the own slice (rwkv.cu:513-524) --------------------------------
     {
@@ -636,7 +666,7 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
         const double x2 = (double)sqrtf((float)qtot / (float)(E - 1));
         tok_sync(); // scratch is reused by owners_reduce below
         if (mine) sm.xown[ctid] = p.ln[j] * (((double)row[j] - xmean) / x2) + p.ln[E + j];
-        publish_stats(sm, statp(q), ne, rd, ctid);
+        publish_stats(p, sm, phase, ne, rd, ctid);
     }
     // parameters of the first LN1 / token-shift slice computation
     double lw = 0, lb = 0, mk = 0, mv = 0, mr = 0, st = 0;
@@ -655,7 +685,7 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
     };
     if (p.L_run > 0) prefetch_att(0, j0, so0);
     stamp();
-    grid_sync(p.gbar, target, ctid);
+    grid_sync(p, target, phase, ctid);
     stamp();
     ++q;
 
@@ -667,7 +697,7 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
         // ======== LN1 + token shift for the own slice (rwkv.cu:535-540) ==========================
         {
             double xmean = 0.0, x2 = 1.0;
-            if (warp < nwe) stats_from_parts(p, statp(q - 1), lane, xmean, x2);
+            if (warp < nwe) stats_from_acc(p, acc_buf(p, phase - 1), xmean, x2);
             double mx[3] = {0, 0, 0}, of[3] = {0, 0, 0};
             if (mine) {
                 const double ln = lw * ((sm.xown[ctid] - xmean) * (1.0 / x2)) + lb;
@@ -678,21 +708,21 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
                 const float xv = (float)((double)fv * (double)rv);
                 const float xr = (float)((double)fr * (double)rr);
                 float *vec = vecp(q);
-                vec[j] = xk;
-                vec[E + j] = xv;
-                vec[2 * E + j] = xr;
+                put(vec + j, xk);
+                put(vec + E + j, xv);
+                put(vec + 2 * E + j, xr);
                 mx[0] = fabs((double)xk); mx[1] = fabs((double)xv); mx[2] = fabs((double)xr);
                 of[0] = (double)fk * (double)ok; of[1] = (double)fv * (double)ov; of[2] = (double)fr * (double)orr;
                 p.sxy[so + lo + j] = ln; // only the owner ever reads or writes this element
             }
-            publish_vparts<3>(vpartp(q), mx, of, rd, ctid, ne);
+            publish_vparts<3>(p, phase, mx, of, rd, ctid, ne);
         }
         stamp();
-    grid_sync(p.gbar, target, ctid);
+    grid_sync(p, target, phase, ctid);
     stamp();
         ++q;
         // ======== K, V, R GEMVs for the own channels + WKV (rwkv.cu:542-545) =====================
-        gather_quantise(sm.planes, sm.scal, vecp(q - 1), vpartp(q - 1), 3, E, ctid, p.trace);
+        gather_quantise(sm.planes, sm.scal, vecp(q - 1), acc_buf(p, phase - 1), 3, E, ctid, gb, gn, p.trace);
         stamp();
         {
 #ifndef RK_EXP1
@@ -742,18 +772,18 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
                 p.sbb[so + lo + j] = (bb + ek) * ew;
                 const float rw = (float)y;
                 const float xo = (float)((double)rw * (double)ro);
-                vecp(q)[j] = xo;
+                put(vecp(q) + j, xo);
                 mx[0] = fabs((double)xo);
                 of[0] = (double)rw * (double)oco;
             }
-            publish_vparts<1>(vpartp(q), mx, of, rd, ctid, ne);
+            publish_vparts<1>(p, phase, mx, of, rd, ctid, ne);
         }
         stamp();
-    grid_sync(p.gbar, target, ctid);
+    grid_sync(p, target, phase, ctid);
     stamp();
         ++q;
         // ======== out-projection + residual (rwkv.cu:548-553) =====================================
-        gather_quantise(sm.planes, sm.scal, vecp(q - 1), vpartp(q - 1), 1, E, ctid, p.trace);
+        gather_quantise(sm.planes, sm.scal, vecp(q - 1), acc_buf(p, phase - 1), 1, E, ctid, gb, gn, p.trace);
         stamp();
         // parameters of the LN2 / ffn token-shift slice computation (used two barriers later)
         double flw = 0, flb = 0, fmk = 0, fmr = 0, fst = 0;
@@ -774,15 +804,15 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
             const float xf = (float)sm.xown[ctid] + y;
             sm.xown[ctid] = (double)xf;
         }
-        publish_stats(sm, statp(q), ne, rd, ctid);
+        publish_stats(p, sm, phase, ne, rd, ctid);
         stamp();
-    grid_sync(p.gbar, target, ctid);
+    grid_sync(p, target, phase, ctid);
     stamp();
         ++q;
         // ======== LN2 + token shift for the own slice (rwkv.cu:557-562) ===========================
         {
             double xmean = 0.0, x2 = 1.0;
-            if (warp < nwe) stats_from_parts(p, statp(q - 1), lane, xmean, x2);
+            if (warp < nwe) stats_from_acc(p, acc_buf(p, phase - 1), xmean, x2);
             double mx[3] = {0, 0, 0}, of[3] = {0, 0, 0};
             if (mine) {
                 const double ln = flw * ((sm.xown[ctid] - xmean) * (1.0 / x2)) + flb;
@@ -791,20 +821,20 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
                 const float xr = (float)((double)fr * (double)frr);
                 const float xk = (float)((double)fk * (double)frk);
                 float *vec = vecp(q);
-                vec[j] = xr;
-                vec[E + j] = xk;
+                put(vec + j, xr);
+                put(vec + E + j, xk);
                 mx[0] = fabs((double)xr); mx[1] = fabs((double)xk);
                 of[0] = (double)fr * (double)forr; of[1] = (double)fk * (double)fok;
                 p.sdd[so + lo + j] = ln;
             }
-            publish_vparts<2>(vpartp(q), mx, of, rd, ctid, ne);
+            publish_vparts<2>(p, phase, mx, of, rd, ctid, ne);
         }
         stamp();
-    grid_sync(p.gbar, target, ctid);
+    grid_sync(p, target, phase, ctid);
     stamp();
         ++q;
         // ======== ffn R (own slice rows) and ffn K (4E rows) + sigmoid / relu^2 (rwkv.cu:566-573) ==
-        gather_quantise(sm.planes, sm.scal, vecp(q - 1), vpartp(q - 1), 2, E, ctid, p.trace);
+        gather_quantise(sm.planes, sm.scal, vecp(q - 1), acc_buf(p, phase - 1), 2, E, ctid, gb, gn, p.trace);
         stamp();
         {
             float rvk[2] = {0, 0}, ovk[2] = {0, 0}; // ffn-V scale / offset of the own K rows (<= 2 per thread)
@@ -835,19 +865,19 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
                     a = a > 0.0f ? a : 0.0f;
                     a = a * a;
                     const float xv = (float)((double)a * (double)rvk[t]);
-                    vec[sl.k0 + i] = xv;
+                    put(vec + sl.k0 + i, xv);
                     mx[0] = fmax(mx[0], (double)xv);
                     of[0] += (double)a * (double)ovk[t];
                 }
             }
-            publish_vparts<1>(vpartp(q), mx, of, rd, ctid, nk < kRedMax ? nk : kRedMax);
+            publish_vparts<1>(p, phase, mx, of, rd, ctid, nk < kRedMax ? nk : kRedMax);
         }
         stamp();
-    grid_sync(p.gbar, target, ctid);
+    grid_sync(p, target, phase, ctid);
     stamp();
         ++q;
         // ======== ffn V (rows of 4E bytes, four warps per row) + residual (rwkv.cu:574-577) =========
-        gather_quantise(sm.planes, sm.scal, vecp(q - 1), vpartp(q - 1), 1, 4 * E, ctid, p.trace);
+        gather_quantise(sm.planes, sm.scal, vecp(q - 1), acc_buf(p, phase - 1), 1, 4 * E, ctid, gb, gn, p.trace);
         stamp();
         rp = consume_sub<CPL, FULL, 4>(c_ring, c_full, c_empty, c_tile, c_stages, c_planes + (uint32_t)(0), c_res + (uint32_t)(0) * 8u, 4 * E, sl.e1 - sl.e0, rp, c_warp, c_lane, c_ptrace, c_tcnt);
         // issued after the register-hungry core; the loads land during the epilogue + grid barrier
@@ -858,9 +888,9 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
             const float kv = (float)(sm.scal[0] * row_total(0, ctid, 4 * 1) + sm.scal[3]);
             sm.xown[ctid] = sm.xown[ctid] + (double)(kv * sm.srown[ctid]);
         }
-        publish_stats(sm, statp(q), ne, rd, ctid);
+        publish_stats(p, sm, phase, ne, rd, ctid);
         stamp();
-    grid_sync(p.gbar, target, ctid);
+    grid_sync(p, target, phase, ctid);
     stamp();
         ++q;
     }
@@ -868,24 +898,24 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
     // ======== LN_out for the own slice, head GEMV (rwkv.cu:585-589) ================================
     {
         double xmean = 0.0, x2 = 1.0;
-        if (warp < nwe) stats_from_parts(p, statp(q - 1), lane, xmean, x2);
+        if (warp < nwe) stats_from_acc(p, acc_buf(p, phase - 1), xmean, x2);
         double mx[3] = {0, 0, 0}, of[3] = {0, 0, 0};
         if (mine) {
             const double *lwp = p.ln + (size_t)(4 * p.L + 2) * E;
             const float f = (float)(lwp[j] * ((sm.xown[ctid] - xmean) * (1.0 / x2)) + lwp[E + j]);
             const float xh = (float)((double)f * (double)p.rhead[j]);
-            vecp(q)[j] = xh;
+            put(vecp(q) + j, xh);
             mx[0] = fabs((double)xh);
             of[0] = (double)f * (double)p.ochead[j];
             p.x[j] = sm.xown[ctid]; // residual stream after the last layer (debug / tests)
         }
-        publish_vparts<1>(vpartp(q), mx, of, rd, ctid, ne);
+        publish_vparts<1>(p, phase, mx, of, rd, ctid, ne);
     }
     stamp();
-    grid_sync(p.gbar, target, ctid);
+    grid_sync(p, target, phase, ctid);
     stamp();
     ++q;
-    gather_quantise(sm.planes, sm.scal, vecp(q - 1), vpartp(q - 1), 1, E, ctid, p.trace);
+    gather_quantise(sm.planes, sm.scal, vecp(q - 1), acc_buf(p, phase - 1), 1, E, ctid, gb, gn, p.trace);
     stamp();
     rp = consume_sub<CPL, FULL, 1>(c_ring, c_full, c_empty, c_tile, c_stages, c_planes + (uint32_t)(0), c_res + (uint32_t)(0) * 8u, E, sl.v1 - sl.v0, rp, c_warp, c_lane, c_ptrace, c_tcnt);
     tok_sync();
@@ -895,7 +925,7 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
         int bidx = 0x7fffffff;
         for (int i = ctid; i < sl.nv; i += kTokConsumers) {
             const float y = (float)(sm.scal[0] * row_total(0, i, 1) + sm.scal[3]);
-            p.logits[sl.v0 + i] = y;
+            put(p.logits + sl.v0 + i, y);
             if (y > best) { // i ascending per thread: first maximum kept
                 best = y;
                 bidx = sl.v0 + i;
@@ -926,33 +956,22 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
                         best = bv[w];
                         bidx = bi[w];
                     }
-                p.amax_val[blockIdx.x] = best;
-                p.amax_idx[blockIdx.x] = bidx;
+                if (bidx != 0x7fffffff) {
+                    // order-preserving image of the float above ~index: max = largest logit, then smallest index
+                    unsigned int u = __float_as_uint(best);
+                    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+                    const unsigned long long key = ((unsigned long long)u << 32) | (unsigned long long)(0xffffffffu - (unsigned int)bidx);
+                    unsigned long long *acc = acc_buf(p, phase);
+                    for (int g = 0; g < p.tp_size; ++g) red_max_u64(peer_ptr(p, acc, g) + kAccArg, key, sys);
+                }
             }
             stamp();
-    grid_sync(p.gbar, target, ctid);
+    grid_sync(p, target, phase, ctid);
     stamp();
-            if (blockIdx.x == 0 && warp == 0) {
-                float b2 = -INFINITY;
-                int i2 = 0x7fffffff;
-                for (int c = lane; c < (int)gridDim.x; c += 32) {
-                    const float v = __ldcg(p.amax_val + c);
-                    const int ix = __ldcg(p.amax_idx + c);
-                    if (v > b2 || (v == b2 && ix < i2)) {
-                        b2 = v;
-                        i2 = ix;
-                    }
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    const float ov2 = __shfl_xor_sync(0xffffffffu, b2, o);
-                    const int oi = __shfl_xor_sync(0xffffffffu, i2, o);
-                    if (ov2 > b2 || (ov2 == b2 && oi < i2)) {
-                        b2 = ov2;
-                        i2 = oi;
-                    }
-                }
-                if (lane == 0) ctrl->next = (unsigned long long)(i2 == 0x7fffffff ? 0 : i2);
+            if (blockIdx.x == 0 && ctid == 0) {
+                const unsigned long long key = __ldcg(acc_buf(p, phase - 1) + kAccArg);
+                const unsigned int ix = 0xffffffffu - (unsigned int)(key & 0xffffffffull);
+                ctrl->next = (unsigned long long)(key == 0ull ? 0u : ix);
             }
         }
     }
