@@ -195,6 +195,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=None, choices=sorted(SHAPES))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--parallelism", default="tp", choices=["tp", "replicas"],
+                    help="N > 1: 'tp' = ONE stream tensor-parallel over the N GPUs (strong scaling); "
+                         "'replicas' = N independent streams (weak scaling)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -224,7 +227,12 @@ def main():
     if dist is not None:
         dist.barrier()
     path = model_path(workload, pkg)
-    eng = pkg.Engine(path, device=local_rank)
+    tp = world > 1 and args.parallelism == "tp"
+    if tp:
+        eng = pkg.Engine(path, device=local_rank, tp_rank=rank, tp_size=world)
+        pkg.tp.connect(eng)
+    else:
+        eng = pkg.Engine(path, device=local_rank)
 
     # ---- warm-up (also builds the CUDA graphs) -------------------------------------------
     eng.state_zero()
@@ -250,7 +258,7 @@ def main():
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
-    tokens_total = args.steps * world  # independent streams per rank until the sharded path lands
+    tokens_total = args.steps if tp else args.steps * world  # tp: one stream over all GPUs; replicas: one per GPU
     value = tokens_total / (ms / 1e3)
 
     # ---- e2e: the user-facing call with host buffers -------------------------------------
@@ -270,7 +278,20 @@ def main():
     e2e_value = tokens_total / float(t.item())
     clocks = sampler.finish() if rank == 0 else None
 
+    def prof_run():
+        eng.state_zero()
+        toks = [SEED_TOKEN]
+        tk = SEED_TOKEN
+        for _ in range(7):
+            tk = int(eng.forward([tk])[0].argmax())
+            toks.append(tk)
+        eng.state_zero()
+        return toks, eng.profile(toks)
+
     if rank != 0:
+        if tp:
+            prof_run()  # every rank of a tensor-parallel group must launch what rank 0 launches
+            dist.barrier()
         eng.close()
         if dist is not None:
             dist.barrier()
@@ -278,14 +299,9 @@ def main():
         return
 
     # ---- per-kernel roofline (launch-by-launch, CUDA events around every launch) ---------
-    eng.state_zero()
-    prof_tokens = [SEED_TOKEN]
-    tk = SEED_TOKEN
-    for _ in range(7):
-        tk = int(eng.forward([tk])[0].argmax())
-        prof_tokens.append(tk)
-    eng.state_zero()
-    prof = eng.profile(prof_tokens)
+    prof_tokens, prof = prof_run()
+    if tp:
+        dist.barrier()
     peak, peak_src = measured_peak()
     kernels = {}
     total_ms = sum(v["ms_sum"] for v in prof.values()) or 1.0
@@ -294,15 +310,16 @@ def main():
             continue
         dur_ms = v["ms_sum"] / v["launches"]
         kernels[name] = {"launches_per_token": v["launches"] // len(prof_tokens), "us_per_launch": round(dur_ms * 1e3, 3),
-                         "bytes_per_launch": int(v["bytes_per_launch"]),
-                         "gbs": round(v["bytes_per_launch"] / dur_ms / 1e6, 1), "share": round(v["ms_sum"] / total_ms, 4)}
+                         "bytes_per_launch": int(v["bytes_per_launch"] / (world if tp else 1)),
+                         "gbs": round(v["bytes_per_launch"] / (world if tp else 1) / dur_ms / 1e6, 1),
+                         "share": round(v["ms_sum"] / total_ms, 4)}
     dom = max(kernels, key=lambda k: kernels[k]["share"])
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s",
                 "frac": round(kernels[dom]["gbs"] / peak, 4), "traffic": ncu_traffic(dom, workload), "peak_source": peak_src,
                 "how": "algorithmic bytes per launch / mean CUDA-event duration per launch (eager profile run, %d tokens)" % len(prof_tokens)}
     abytes = algorithmic_bytes_per_token(L, E)
     cb = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         cb = cpu_baseline(path, prof_tokens)
     eng.close()
 
@@ -310,14 +327,18 @@ def main():
         "metric": "tokens/sec single-stream decode RWKV-4 7B uint8; achieved HBM GB/s vs peak" if workload == "7b"
         else "tokens/sec single-stream decode RWKV-4 %s uint8; achieved HBM GB/s vs peak" % workload,
         "value": round(value, 2), "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": round(ms / args.steps, 5), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": round(ms / args.steps, 5), "higher_is_better": True, "scaling": "strong" if tp else "weak", "vs_baseline": None,
         "dtype": "u8 weights x 23-bit fixed-point activations (byte limbs u8,u8,s8; exact int32 dp4a accumulate), f64 elementwise",
         "data": "synthetic",
         "config": {"workload": "RWKV-4 %s shape (L=%d, E=%d, V=50277) uint8, random-init reference-format .bin, greedy single-stream decode, batch 1" % (workload, L, E),
                    "l2": "inputs larger than L2: %.2f GB of weights per token vs 126 MB L2" % (abytes / 1e9),
-                   "parallelism": "1 stream per GPU" if world > 1 else "1 GPU"},
+                   "parallelism": ("tp%d: one stream, rows of every matrix split over %d x 148 CTAs, peer stores + system-scope "
+                                   "grid barrier over NVLink, no NCCL on the data path" % (world, world)) if tp
+                   else ("replicas: 1 independent stream per GPU" if world > 1 else "1 GPU")},
+        # per-GPU rate: tp -> each GPU streams 1/N of the bytes of every token; replicas -> 1/N of the tokens
         "hbm": {"algorithmic_bytes_per_token": abytes, "achieved_gbs": round(abytes * (value / world) / 1e9, 1),
-                "frac_of_peak": round(abytes * (value / world) / 1e9 / peak, 4), "peak_gbs": peak, "peak_source": peak_src},
+                "frac_of_peak": round(abytes * (value / world) / 1e9 / peak, 4), "peak_gbs": peak, "peak_source": peak_src,
+                "per": "GPU"},
         "roofline": roofline, "kernels": kernels,
         "e2e": {"value": round(e2e_value, 2), "unit": "tokens/s", "h2d_bytes_per_step": 32, "d2h_bytes_per_step": VOCAB * 4,
                 "api": "rwkv_b200_forward(model, &token, 1, GPT, host_logits) + host argmax"},

@@ -9,3 +9,4 @@ ABI) plus build helpers. The directory name contains a hyphen, so import it with
 """
 from .engine import Engine, EngineError, lib_path, load_library  # noqa: F401
 from . import build as build  # noqa: F401
+from . import tp as tp  # noqa: F401

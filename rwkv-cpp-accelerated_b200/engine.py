@@ -83,18 +83,36 @@ class Engine:
     """One loaded model on one GPU. Mirrors the reference's RWKV host class at the
     granularity the tests need: load, forward(tokens, mode), host<->device state."""
 
-    def __init__(self, path, max_gpt=1, device=0, quiet=True):
+    def __init__(self, path, max_gpt=1, device=0, quiet=True, tp_rank=0, tp_size=1):
+        """tp_size > 1: this process is rank `tp_rank` of a tensor-parallel group (one GPU per rank); wire the
+        ranks with tp.connect(engine) before the first forward (include/rwkv_b200.h, "tensor-parallel wiring")."""
         self.lib = load_library()
         if self.lib.rwkv_b200_device_count() <= 0:
             raise EngineError("no CUDA device visible; the B200 engine has no CPU fallback")
         h = ctypes.c_void_p()
         L, E = ctypes.c_ulonglong(), ctypes.c_ulonglong()
-        rc = self.lib.rwkv_b200_load(path.encode(), max_gpt, device, 1 if quiet else 0,
-                                     ctypes.byref(h), ctypes.byref(L), ctypes.byref(E))
+        rc = self.lib.rwkv_b200_load_tp(path.encode(), max_gpt, device, 1 if quiet else 0, tp_rank, tp_size,
+                                        ctypes.byref(h), ctypes.byref(L), ctypes.byref(E))
         if rc != 0:
             raise EngineError("rwkv_b200_load(%s) failed [%d]: %s" % (path, rc, self._err()))
         self.h = h
         self.n_layers, self.n_embed, self.max_gpt = L.value, E.value, max_gpt
+        self.tp_rank, self.tp_size = tp_rank, tp_size
+
+    # -- tensor-parallel wiring ------------------------------------------------------------
+    def tp_export(self):
+        """CUDA IPC handle (64 bytes) of this rank's exchange block."""
+        buf = (ctypes.c_ubyte * 64)()
+        self._ck(self.lib.rwkv_b200_tp_export(self.h, ctypes.cast(buf, ctypes.c_void_p)), "tp_export")
+        return bytes(buf)
+
+    def tp_import(self, handles):
+        """handles: one 64-byte handle per rank, in rank order (the own entry is ignored)."""
+        if len(handles) != self.tp_size or any(len(x) != 64 for x in handles):
+            raise EngineError("tp_import needs %d handles of 64 bytes" % self.tp_size)
+        blob = b"".join(handles)
+        buf = (ctypes.c_ubyte * len(blob)).from_buffer_copy(blob)
+        self._ck(self.lib.rwkv_b200_tp_import(self.h, ctypes.cast(buf, ctypes.c_void_p)), "tp_import")
 
     def _err(self):
         return self.lib.rwkv_b200_last_error().decode(errors="replace")
