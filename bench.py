@@ -195,9 +195,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=None, choices=sorted(SHAPES))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--parallelism", default="tp", choices=["tp", "replicas"],
-                    help="N > 1: 'tp' = ONE stream tensor-parallel over the N GPUs (strong scaling); "
-                         "'replicas' = N independent streams (weak scaling)")
+    ap.add_argument("--parallelism", default="replicas", choices=["tp", "replicas"],
+                    help="N > 1: which arrangement the headline `value` reports. 'replicas' = N independent streams, "
+                         "one per GPU (weak scaling, no data-path collective); 'tp' = ONE stream tensor-parallel over "
+                         "the N GPUs (strong scaling). The other arrangement is measured too and reported under `alt`.")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -219,6 +220,8 @@ def main():
     if world > 1:
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
+        # stdout carries ONE JSON line: NCCL's version banner / debug lines go to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     L, E = SHAPES[workload]
@@ -228,11 +231,15 @@ def main():
         dist.barrier()
     path = model_path(workload, pkg)
     tp = world > 1 and args.parallelism == "tp"
-    if tp:
-        eng = pkg.Engine(path, device=local_rank, tp_rank=rank, tp_size=world)
-        pkg.tp.connect(eng)
-    else:
-        eng = pkg.Engine(path, device=local_rank)
+
+    def make_engine(as_tp):
+        if as_tp:
+            e = pkg.Engine(path, device=local_rank, tp_rank=rank, tp_size=world)
+            pkg.tp.connect(e)
+            return e
+        return pkg.Engine(path, device=local_rank)
+
+    eng = make_engine(tp)
 
     # ---- warm-up (also builds the CUDA graphs) -------------------------------------------
     eng.state_zero()
@@ -278,6 +285,25 @@ def main():
     e2e_value = tokens_total / float(t.item())
     clocks = sampler.finish() if rank == 0 else None
 
+    # ---- N > 1: also time the other arrangement of the same N GPUs ---------------------------------
+    alt = None
+    if world > 1:
+        other = make_engine(not tp)
+        other.decode_timed([SEED_TOKEN] * args.warmup, teacher_forced=False)
+        other.state_zero()
+        sync_all()
+        ms1 = other.decode_timed([SEED_TOKEN] * args.steps, teacher_forced=False)
+        sync_all()
+        other.close()
+        t = torch.tensor([ms1], dtype=torch.float64, device="cuda:%d" % local_rank)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        n_tok = args.steps * world if tp else args.steps
+        alt = {"parallelism": ("replicas: %d independent streams, one per GPU (weak scaling)" % world) if tp
+               else ("tp%d: ONE stream over %d GPUs (strong scaling; rows of every matrix split over %d x 148 CTAs, peer "
+                     "stores + system-scope grid barrier over NVLink, no NCCL on the data path)" % (world, world, world)),
+               "value": round(n_tok / (float(t.item()) / 1e3), 2), "unit": "tokens/s",
+               "ms_per_token_per_stream": round(float(t.item()) / args.steps, 5)}
+
     def prof_run():
         eng.state_zero()
         toks = [SEED_TOKEN]
@@ -315,7 +341,7 @@ def main():
                          "share": round(v["ms_sum"] / total_ms, 4)}
     dom = max(kernels, key=lambda k: kernels[k]["share"])
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s",
-                "frac": round(kernels[dom]["gbs"] / peak, 4), "traffic": ncu_traffic(dom, workload), "peak_source": peak_src,
+                "frac": round(kernels[dom]["gbs"] / peak, 4), "traffic": ncu_traffic(dom, workload) if world == 1 else None, "peak_source": peak_src,
                 "how": "algorithmic bytes per launch / mean CUDA-event duration per launch (eager profile run, %d tokens)" % len(prof_tokens)}
     abytes = algorithmic_bytes_per_token(L, E)
     cb = None
@@ -344,6 +370,8 @@ def main():
                 "api": "rwkv_b200_forward(model, &token, 1, GPT, host_logits) + host argmax"},
         "gpu_launches": int(launches), "clocks": clocks, "cpu_baseline": cb,
     }
+    if alt is not None:
+        out["alt"] = alt
     print(json.dumps(out))
     if dist is not None:
         dist.barrier()

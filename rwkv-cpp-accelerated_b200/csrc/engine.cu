@@ -472,7 +472,7 @@ int do_load(M *m, const char *path, int quiet) {
         (rc = dmalloc(m, &b3, E)))
         return rc;
     CK(cudaMemsetAsync(p.ctrl, 0, sizeof(rk::Ctrl), m->stream));
-    // exchange block: [0,128) barrier counter | [128,512) accumulators | [1024, +32E) vec | logits
+    // exchange block: [0,64) barrier counter, [64,128) rank-local arrival counter | [128,512) accumulators | [1024, +32E) vec | logits
     {
         unsigned char *x = nullptr;
         m->xch_bytes = (1024 + 32 * (size_t)E + 4 * (size_t)binfmt::kVocab + 255) & ~(size_t)255;
@@ -480,6 +480,7 @@ int do_load(M *m, const char *path, int quiet) {
         CK(cudaMemsetAsync(x, 0, m->xch_bytes, m->stream));
         for (int g = 0; g < 8; ++g) p.xch[g] = x; // peers are wired by rwkv_b200_tp_import
         p.gbar = reinterpret_cast<unsigned int *>(x);
+        p.lbar = reinterpret_cast<unsigned int *>(x + 64);
         p.acc = reinterpret_cast<unsigned long long *>(x + 128);
         p.vec = reinterpret_cast<float *>(x + 1024);
         p.logits = reinterpret_cast<float *>(x + 1024 + 32 * (size_t)E);

@@ -88,7 +88,8 @@ struct Params {
     // The exchange block of this rank (one allocation, peer-mapped by the other ranks): gbar, acc,
     // vec and logits all point into xch[tp_rank]; xch[g] is rank g's block as seen from here.
     unsigned char *xch[8];
-    unsigned int *gbar;                // grid barrier counter (monotonic, counts the CTAs of all ranks)
+    unsigned int *gbar;                // grid barrier counter (monotonic; one rank: counts CTAs, several: counts ranks)
+    unsigned int *lbar;                // rank-local arrival counter of the hierarchical barrier (tp_size > 1)
     unsigned long long *acc;           // [3 phases][16] integer accumulators (token_kernel.cuh)
     float *vec;                        // [2 parity][4E] next-phase activation vector(s), pre-scaled by r
     unsigned long long *trace;         // optional [grid][kTraceMax] globaltimer stamps (debug), or nullptr

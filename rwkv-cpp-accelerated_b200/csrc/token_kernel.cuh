@@ -134,27 +134,41 @@ __device__ __forceinline__ unsigned long long *acc_buf(const Params &p, unsigned
 }
 
 // Grid barrier over the consumer threads of all CTAs of all ranks (the producer warps do not take
-// part). Afterwards CTA 0 clears the accumulator buffer that the phase after next will write.
-__device__ __forceinline__ void grid_sync(const Params &p, unsigned int &target, unsigned int &phase, int ctid) {
+// part). `phase` = number of barriers completed so far (monotonic across launches, Ctrl::bar_base);
+// it also selects the accumulator buffer. One rank: every CTA adds 1 to gbar and waits for
+// phase*grid. Several ranks, hierarchical: every CTA arrives on the rank-local counter lbar (an
+// acq_rel RMW chain, at system scope so that the CTA's own peer stores are acknowledged first);
+// the last local arriver adds 1 to gbar of EVERY rank; everybody waits for phase*ranks on the own
+// gbar. (Flat all-to-all increments made each counter take ranks*148 remote atomics per barrier:
+// 6.6 us per barrier on 2 GPUs, 14.7 us on 4.)
+// Afterwards CTA 0 clears the accumulator buffer that the phase after next will write.
+__device__ __forceinline__ void grid_sync(const Params &p, unsigned int &phase, int ctid) {
     tok_sync();
-    const bool sys = p.tp_size > 1;
-    target += gridDim.x * (unsigned int)p.tp_size;
+    ++phase;
     if (ctid == 0) {
-        // release: everything this CTA wrote (ordered before by the bar.sync above) is visible to any
-        // thread that observes the increment with an acquire load.
-        if (sys) {
-            for (int g = 0; g < p.tp_size; ++g)
-                asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(peer_ptr(p, p.gbar, g)) : "memory");
-        } else {
-            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.gbar) : "memory");
-        }
         unsigned int spins = 0;
-        while ((int)(ld_acquire_u32(p.gbar, sys) - target) < 0) {
-            if (++spins > (1u << 25)) __trap();
+        if (p.tp_size == 1) {
+            // release: everything this CTA wrote (ordered before by the bar.sync above) is visible to
+            // any thread that observes the increment with an acquire load.
+            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.gbar) : "memory");
+            const unsigned int target = phase * gridDim.x;
+            while ((int)(ld_acquire_u32(p.gbar, false) - target) < 0) {
+                if (++spins > (1u << 25)) __trap();
+            }
+        } else {
+            unsigned int old;
+            asm volatile("atom.acq_rel.sys.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(p.lbar) : "memory");
+            if (old + 1u == phase * gridDim.x) {
+                for (int g = 0; g < p.tp_size; ++g)
+                    asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(peer_ptr(p, p.gbar, g)) : "memory");
+            }
+            const unsigned int target = phase * (unsigned int)p.tp_size;
+            while ((int)(ld_acquire_u32(p.gbar, true) - target) < 0) {
+                if (++spins > (1u << 25)) __trap();
+            }
         }
     }
     tok_sync();
-    ++phase;
     if (blockIdx.x == 0 && ctid < kAccSlots) acc_buf(p, phase + 1)[ctid] = 0ull;
 }
 
@@ -598,14 +612,13 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
     const int j0 = sl.e0 + (mine ? ctid : 0);
     const int j = j0;
     Ctrl *ctrl = p.ctrl;
-    unsigned int target = ctrl->bar_base;
+    unsigned int phase = ctrl->bar_base;             // barriers completed so far: phase number, selects the accumulator buffer
     unsigned long long token = ctrl->token;
     if (p.feed_mode == 1) token = ctrl->next;
     else if (p.feed_mode == 2) token = p.stream[ctrl->pos];
     const size_t so0 = (size_t)ctrl->slot * p.L * E; // state slot offset
     const size_t so = so0;
     unsigned int q = 0;                              // exchange-buffer parity counter (one per barrier)
-    unsigned int phase = target / (unsigned int)gn;  // global phase number: selects the accumulator buffer
     const bool sys = p.tp_size > 1;
     RingPos rp{0, 0};
     const uint32_t c_ring = opaque(smem_u32(sm.ring)), c_full = opaque(smem_u32(sm.full)),
@@ -685,7 +698,7 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
     };
     if (p.L_run > 0) prefetch_att(0, j0, so0);
     stamp();
-    grid_sync(p, target, phase, ctid);
+    grid_sync(p, phase, ctid);
     stamp();
     ++q;
 
@@ -718,7 +731,7 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
             publish_vparts<3>(p, phase, mx, of, rd, ctid, ne);
         }
         stamp();
-    grid_sync(p, target, phase, ctid);
+    grid_sync(p, phase, ctid);
     stamp();
         ++q;
         // ======== K, V, R GEMVs for the own channels + WKV (rwkv.cu:542-545) =====================
@@ -779,7 +792,7 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
             publish_vparts<1>(p, phase, mx, of, rd, ctid, ne);
         }
         stamp();
-    grid_sync(p, target, phase, ctid);
+    grid_sync(p, phase, ctid);
     stamp();
         ++q;
         // ======== out-projection + residual (rwkv.cu:548-553) =====================================
@@ -806,7 +819,7 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
         }
         publish_stats(p, sm, phase, ne, rd, ctid);
         stamp();
-    grid_sync(p, target, phase, ctid);
+    grid_sync(p, phase, ctid);
     stamp();
         ++q;
         // ======== LN2 + token shift for the own slice (rwkv.cu:557-562) ===========================
@@ -830,7 +843,7 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
             publish_vparts<2>(p, phase, mx, of, rd, ctid, ne);
         }
         stamp();
-    grid_sync(p, target, phase, ctid);
+    grid_sync(p, phase, ctid);
     stamp();
         ++q;
         // ======== ffn R (own slice rows) and ffn K (4E rows) + sigmoid / relu^2 (rwkv.cu:566-573) ==
@@ -873,7 +886,7 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
             publish_vparts<1>(p, phase, mx, of, rd, ctid, nk < kRedMax ? nk : kRedMax);
         }
         stamp();
-    grid_sync(p, target, phase, ctid);
+    grid_sync(p, phase, ctid);
     stamp();
         ++q;
         // ======== ffn V (rows of 4E bytes, four warps per row) + residual (rwkv.cu:574-577) =========
@@ -890,7 +903,7 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
         }
         publish_stats(p, sm, phase, ne, rd, ctid);
         stamp();
-    grid_sync(p, target, phase, ctid);
+    grid_sync(p, phase, ctid);
     stamp();
         ++q;
     }
@@ -912,7 +925,7 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
         publish_vparts<1>(p, phase, mx, of, rd, ctid, ne);
     }
     stamp();
-    grid_sync(p, target, phase, ctid);
+    grid_sync(p, phase, ctid);
     stamp();
     ++q;
     gather_quantise(sm.planes, sm.scal, vecp(q - 1), acc_buf(p, phase - 1), 1, E, ctid, gb, gn, p.trace);
@@ -966,7 +979,7 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
                 }
             }
             stamp();
-    grid_sync(p, target, phase, ctid);
+    grid_sync(p, phase, ctid);
     stamp();
             if (blockIdx.x == 0 && ctid == 0) {
                 const unsigned long long key = __ldcg(acc_buf(p, phase - 1) + kAccArg);
@@ -976,7 +989,7 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
         }
     }
     if (blockIdx.x == 0 && ctid == 0) {
-        ctrl->bar_base = target;
+        ctrl->bar_base = phase;
         if (p.feed_mode == 2) ctrl->pos = ctrl->pos + 1;
     }
 }
