@@ -53,9 +53,14 @@ int rwkv_b200_load(const char *path, unsigned long long max_gpt, int device, int
                    rwkv_b200_model **out, unsigned long long *n_layers,
                    unsigned long long *n_embed);
 
-/* Tensor-parallel load: this process owns shard `tp_rank` of `tp_size` (see
- * DESIGN.md "multi-GPU"); `tp_size` = 1 is identical to rwkv_b200_load. No
- * reference counterpart (the reference is single-GPU). */
+/* Tensor-parallel load: this process is rank `tp_rank` of `tp_size` (1..8) ranks,
+ * one GPU each, that decode ONE stream together: the rows of
+ * every matrix are split over the tp_size x 148 CTAs of all ranks; weights are
+ * replicated, each rank streams only its rows. Every rank must then make the same
+ * forward calls with the same tokens; all of them receive the same logits.
+ * `tp_size` = 1 is identical to rwkv_b200_load. After loading, wire the ranks with
+ * rwkv_b200_tp_export / rwkv_b200_tp_import before the first forward.
+ * No reference counterpart (the reference is single-GPU). */
 int rwkv_b200_load_tp(const char *path, unsigned long long max_gpt, int device, int quiet,
                       int tp_rank, int tp_size, rwkv_b200_model **out,
                       unsigned long long *n_layers, unsigned long long *n_embed);
@@ -150,7 +155,8 @@ int rwkv_b200_set_option(rwkv_b200_model *m, const char *key, const char *value)
 
 /* --- tensor-parallel wiring (tp_size > 1 only) --------------------------------- */
 
-/* Size in bytes of the peer-visible exchange buffer each rank must allocate. */
+/* Size in bytes of this rank's peer-visible exchange block (barrier counters,
+ * accumulators, activation vectors, logits); allocated by the load. */
 size_t rwkv_b200_tp_buffer_bytes(const rwkv_b200_model *m);
 /* Export this rank's exchange buffer as a CUDA IPC handle (64 bytes). */
 int rwkv_b200_tp_export(rwkv_b200_model *m, void *ipc_handle_64);
