@@ -175,8 +175,8 @@ def run_reference(args, pkg, workload):
 
 def ncu_traffic(kernel, workload):
     """DRAM bytes (read + write) per launch of the dominant kernel, from the committed `ncu --set full`
-    capture of the same command (profiles/r01d_token_traffic.json); null if there is none for this case."""
-    p = os.path.join(ROOT, "profiles", "r01d_token_traffic.json")
+    capture of the same command (profiles/r01f_token_traffic.json); null if there is none for this case."""
+    p = os.path.join(ROOT, "profiles", "r01f_token_traffic.json")
     try:
         with open(p) as f:
             t = json.load(f)
