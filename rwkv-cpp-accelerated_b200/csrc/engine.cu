@@ -114,12 +114,15 @@ template <int CPL> int set_attrs(size_t smem) {
     return 0;
 }
 template <int CPL> int set_attrs_tok(size_t smem) {
-    CK(cudaFuncSetAttribute(rk::k_token<CPL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CK(cudaFuncSetAttribute(rk::k_token<CPL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(rk::k_token<CPL, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(rk::k_token<CPL, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(rk::k_token<CPL, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(rk::k_token<CPL, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     return 0;
 }
-template <int CPL> const void *token_entry(bool full) {
-    return full ? (const void *)rk::k_token<CPL, true> : (const void *)rk::k_token<CPL, false>;
+template <int CPL> const void *token_entry(bool full, bool trace) {
+    if (trace) return full ? (const void *)rk::k_token<CPL, true, true> : (const void *)rk::k_token<CPL, false, true>;
+    return full ? (const void *)rk::k_token<CPL, true, false> : (const void *)rk::k_token<CPL, false, false>;
 }
 
 struct EventPair {
@@ -192,8 +195,9 @@ int launch_token(M *m, int feed, bool greedy, const unsigned long long *stream, 
     prm.stream = stream;
     void *args[] = {&prm};
     const bool full = m->E == (unsigned long long)m->cpl * 512ull;
-    const void *fn = m->cpl == 2 ? token_entry<2>(full) : m->cpl == 4 ? token_entry<4>(full)
-                   : m->cpl == 8 ? token_entry<8>(full) : token_entry<10>(full);
+    const bool trace = m->p.trace != nullptr;
+    const void *fn = m->cpl == 2 ? token_entry<2>(full, trace) : m->cpl == 4 ? token_entry<4>(full, trace)
+                   : m->cpl == 8 ? token_entry<8>(full, trace) : token_entry<10>(full, trace);
     CK(cudaLaunchCooperativeKernel(fn, dim3(m->grid), dim3(rk::kTokThreads), args, m->smem, s));
     return 0;
 }

@@ -28,18 +28,15 @@ namespace rk {
 // ---- thread layout of the token kernel -------------------------------------------------------
 // Eight consumer warps (two per scheduler, each holding the limbs of one n_embed-byte row segment
 // in registers) + one producer warpgroup: its first lane streams the weights, the rest of it only
-// donates registers through setmaxnreg. RK_TOK_WARPS=16 (two warps per row segment, 104
-// registers) is kept compilable for experiments; it measured slower (spills).
+// donates registers through setmaxnreg. (Sixteen consumer warps with two warps per row segment
+// and a 104-register budget measured slower: spills.)
 #ifndef RK_CORE_INLINE
 #define RK_CORE_INLINE __forceinline__
 #endif
 #ifndef RK_GATHER_INLINE
 #define RK_GATHER_INLINE __noinline__
 #endif
-#ifndef RK_TOK_WARPS
-#define RK_TOK_WARPS 8
-#endif
-constexpr int kTokWarps = RK_TOK_WARPS;       // 8: one warp per row, 232 regs; 16: two warps per row, 104 regs
+constexpr int kTokWarps = 8;                   // one warp per unit of a tile, 232 registers each
 constexpr int kTokConsumers = kTokWarps * 32;
 #ifndef RK_PRODUCER_THREADS
 #define RK_PRODUCER_THREADS 128
@@ -50,15 +47,15 @@ constexpr int kTokConsumers = kTokWarps * 32;
 // ptxas still makes its pre-allocation choices against 168: left alone it re-derives thread ids,
 // shared-window bases and kernel parameters inside every tile iteration and keeps one shared
 // load in flight (ncu r01d: 45 % of the core's samples). The hot loop therefore takes its
-// operands through opaque() - values the optimiser cannot rematerialise - and pins its loads.
+// operands through opaque() - values the optimiser cannot rematerialise.
 constexpr int kProducerThreads = RK_PRODUCER_THREADS;
 constexpr int kTokThreads = kTokConsumers + kProducerThreads;
 constexpr int kProducerRegs = 40;
 // setmaxnreg budget: the consumers may only take what the producer warpgroup gives back
-// (16 warps: compile budget 96, 4 WG x 128 x (104-96) = 4096 <= 128 x (96-40); 8 warps: 168 -> 232).
-constexpr int kConsumerRegs = kTokWarps == 8 ? 232 : 104;
+// (256 x (232 - 168) = 16384 = 128 x (168 - 40)).
+constexpr int kConsumerRegs = 232;
 
-__device__ __forceinline__ void tok_sync() { // named barrier 1: the 16 consumer warps
+__device__ __forceinline__ void tok_sync() { // named barrier 1: the eight consumer warps
     asm volatile("bar.sync 1, %0;" ::"n"(kTokConsumers) : "memory");
 }
 
@@ -152,6 +149,7 @@ __device__ __forceinline__ void grid_sync(const Params &p, unsigned int &phase, 
             // any thread that observes the increment with an acquire load.
             asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.gbar) : "memory");
             const unsigned int target = phase * gridDim.x;
+            // (polling with relaxed loads and one fence.acq_rel after the loop measured 3 % slower)
             while ((int)(ld_acquire_u32(p.gbar, false) - target) < 0) {
                 if (++spins > (1u << 25)) __trap();
             }
@@ -240,7 +238,7 @@ struct RingPos {
 constexpr int kProducers = 1;
 
 __device__ __forceinline__ void produce_sub(const Params &p, const Smem &sm, const int8_t *base, int N, int r0, int r1,
-                                            RingPos &rp, uint64_t policy, int &tcount, int pw) {
+                                            RingPos &rp, uint64_t policy, int &tcount, int pw, unsigned long long *ptrace) {
     const uint32_t ring = smem_u32(sm.ring);
     const uint32_t full0 = smem_u32(sm.full), empty0 = smem_u32(sm.empty);
     const int tr = (8 * p.E) / N; // rows per tile: 8 (N = E) or 2 (N = 4E)
@@ -252,10 +250,10 @@ __device__ __forceinline__ void produce_sub(const Params &p, const Smem &sm, con
             const uint32_t fb = full0 + 8 * rp.stage;
             mbar_expect_tx(fb, bytes);
             bulk_g2s(ring + rp.stage * (uint32_t)p.tile_bytes, base + (size_t)r * N, bytes, fb, policy);
-            if (p.ptrace != nullptr && tcount < kTileTraceMax) {
+            if (ptrace != nullptr && tcount < kTileTraceMax) {
                 unsigned long long t;
                 asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-                p.ptrace[(size_t)blockIdx.x * kTileTraceMax + tcount] = t;
+                ptrace[(size_t)blockIdx.x * kTileTraceMax + tcount] = t;
             }
         }
         ++tcount;
@@ -394,22 +392,27 @@ __device__ __forceinline__ Slices make_slices(int E, int gb, int gn) {
 }
 
 // The producer's whole-token schedule. MUST enumerate subs in exactly the consumers' order.
+// TRACE: the debug time stamps are compiled in (a separate instantiation: the branches alone cost 2 %).
+template <bool TRACE>
 __device__ __forceinline__ void produce_token(const Params &p, const Smem &sm, const Slices &sl, int pw) {
+    unsigned long long *const ptrace = TRACE ? p.ptrace : nullptr;
+    // evict_first keeps the 7 GB/token weight stream from displacing the exchange vectors and the per-layer
+    // parameters in L2: with evict_normal the same kernel runs at 441 instead of 516 tok/s.
     const uint64_t pol = policy_evict_first();
     const int E = p.E;
     RingPos rp{0, 0};
     int tcount = 0;
     for (int l = 0; l < p.L_run; ++l) {
         const size_t mo = (size_t)l * E * E;
-        produce_sub(p, sm, p.wk + mo, E, sl.e0, sl.e1, rp, pol, tcount, pw);
-        produce_sub(p, sm, p.wv + mo, E, sl.e0, sl.e1, rp, pol, tcount, pw);
-        produce_sub(p, sm, p.wr + mo, E, sl.e0, sl.e1, rp, pol, tcount, pw);
-        produce_sub(p, sm, p.wo + mo, E, sl.e0, sl.e1, rp, pol, tcount, pw);
-        produce_sub(p, sm, p.wfr + mo, E, sl.e0, sl.e1, rp, pol, tcount, pw);
-        produce_sub(p, sm, p.wfk + 4 * mo, E, sl.k0, sl.k1, rp, pol, tcount, pw);
-        produce_sub(p, sm, p.wfv + 4 * mo, 4 * E, sl.e0, sl.e1, rp, pol, tcount, pw);
+        produce_sub(p, sm, p.wk + mo, E, sl.e0, sl.e1, rp, pol, tcount, pw, ptrace);
+        produce_sub(p, sm, p.wv + mo, E, sl.e0, sl.e1, rp, pol, tcount, pw, ptrace);
+        produce_sub(p, sm, p.wr + mo, E, sl.e0, sl.e1, rp, pol, tcount, pw, ptrace);
+        produce_sub(p, sm, p.wo + mo, E, sl.e0, sl.e1, rp, pol, tcount, pw, ptrace);
+        produce_sub(p, sm, p.wfr + mo, E, sl.e0, sl.e1, rp, pol, tcount, pw, ptrace);
+        produce_sub(p, sm, p.wfk + 4 * mo, E, sl.k0, sl.k1, rp, pol, tcount, pw, ptrace);
+        produce_sub(p, sm, p.wfv + 4 * mo, 4 * E, sl.e0, sl.e1, rp, pol, tcount, pw, ptrace);
     }
-    produce_sub(p, sm, p.whead, E, sl.v0, sl.v1, rp, pol, tcount, pw);
+    produce_sub(p, sm, p.whead, E, sl.v0, sl.v1, rp, pol, tcount, pw, ptrace);
 }
 
 // mean / std of the full residual stream from the accumulated sum(x), sum(x^2), with the
@@ -517,7 +520,7 @@ __device__ __forceinline__ void trace_stamp2(unsigned long long *trace, double *
 // 24 x 16 B per thread) are issued before anything is consumed, so the whole gather costs ONE L2
 // round trip; every CTA walks the vector from a different starting offset so that the CTAs do not
 // hit the same L2 lines at the same moment.
-constexpr int kGatherBatches = kTokWarps == 8 ? 6 : 3; // x 4 float4 groups x threads x 4 elements >= 4*5120
+constexpr int kGatherBatches = 6; // x 4 float4 groups x 256 threads x 4 elements >= 4*5120
 __device__ RK_GATHER_INLINE void gather_quantise(uint8_t *planes, double *scal, const float *vec,
                                              const unsigned long long *acc, int nvec, int N, int ctid, int rot_num,
                                              int rot_den, unsigned long long *trace) {
@@ -575,8 +578,9 @@ __device__ RK_GATHER_INLINE void gather_quantise(uint8_t *planes, double *scal, 
     tok_sync();
 }
 
-// CPL: 16-byte chunks per lane of one n_embed-byte row segment; FULL: n_embed == CPL*512.
-template <int CPL, bool FULL>
+// CPL: 16-byte chunks per lane of one n_embed-byte row segment; FULL: n_embed == CPL*512;
+// TRACE: with the %globaltimer stamps of tools/trace_token.py (set_option("trace", 1)).
+template <int CPL, bool FULL, bool TRACE>
 __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant__ Params p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const Smem sm = carve(smem_raw, p);
@@ -594,7 +598,7 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp >= kTokWarps) {
         if (kProducerThreads == 128) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kProducerRegs));
-        if (lane == 0 && warp - kTokWarps < kProducers) produce_token(p, sm, sl, warp - kTokWarps);
+        if (lane == 0 && warp - kTokWarps < kProducers) produce_token<TRACE>(p, sm, sl, warp - kTokWarps);
         return;
     }
     if (kProducerThreads == 128) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kConsumerRegs));
@@ -606,7 +610,10 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
         *reinterpret_cast<int *>(sm.scal + 8) = 0;
         *reinterpret_cast<int *>(sm.scal + 9) = 0;
     }
-    auto stamp = [&]() { trace_stamp(p.trace, sm, ctid); };
+    unsigned long long *const c_trace = TRACE ? p.trace : nullptr;
+    auto stamp = [&]() {
+        if (TRACE) trace_stamp(c_trace, sm, ctid);
+    };
     stamp();
     const bool mine = ctid < ne;      // this thread owns residual element j
     const int j0 = sl.e0 + (mine ? ctid : 0);
@@ -626,7 +633,7 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
     const uint32_t c_planes = opaque(smem_u32(sm.planes)), c_res = opaque(smem_u32(sm.res64));
     const uint32_t c_tile = opaque((uint32_t)p.tile_bytes), c_stages = opaque((uint32_t)p.stages);
     const int c_warp = opaque(warp), c_lane = opaque(lane);
-    unsigned long long *const c_ptrace = reinterpret_cast<unsigned long long *>(opaque((size_t)p.ptrace));
+    unsigned long long *const c_ptrace = TRACE ? reinterpret_cast<unsigned long long *>(opaque((size_t)p.ptrace)) : nullptr;
     int *const c_tcnt = reinterpret_cast<int *>(sm.scal + 9);
     // exact integer total of row `i` of the sub whose partials start at res64[off] (nseg per row)
     auto row_total = [&](int off, int i, int nseg) {
@@ -735,7 +742,7 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
     stamp();
         ++q;
         // ======== K, V, R GEMVs for the own channels + WKV (rwkv.cu:542-545) =====================
-        gather_quantise(sm.planes, sm.scal, vecp(q - 1), acc_buf(p, phase - 1), 3, E, ctid, gb, gn, p.trace);
+        gather_quantise(sm.planes, sm.scal, vecp(q - 1), acc_buf(p, phase - 1), 3, E, ctid, gb, gn, c_trace);
         stamp();
         {
 #ifndef RK_EXP1
@@ -796,7 +803,7 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
     stamp();
         ++q;
         // ======== out-projection + residual (rwkv.cu:548-553) =====================================
-        gather_quantise(sm.planes, sm.scal, vecp(q - 1), acc_buf(p, phase - 1), 1, E, ctid, gb, gn, p.trace);
+        gather_quantise(sm.planes, sm.scal, vecp(q - 1), acc_buf(p, phase - 1), 1, E, ctid, gb, gn, c_trace);
         stamp();
         // parameters of the LN2 / ffn token-shift slice computation (used two barriers later)
         double flw = 0, flb = 0, fmk = 0, fmr = 0, fst = 0;
@@ -847,7 +854,7 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
     stamp();
         ++q;
         // ======== ffn R (own slice rows) and ffn K (4E rows) + sigmoid / relu^2 (rwkv.cu:566-573) ==
-        gather_quantise(sm.planes, sm.scal, vecp(q - 1), acc_buf(p, phase - 1), 2, E, ctid, gb, gn, p.trace);
+        gather_quantise(sm.planes, sm.scal, vecp(q - 1), acc_buf(p, phase - 1), 2, E, ctid, gb, gn, c_trace);
         stamp();
         {
             float rvk[2] = {0, 0}, ovk[2] = {0, 0}; // ffn-V scale / offset of the own K rows (<= 2 per thread)
@@ -890,7 +897,7 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
     stamp();
         ++q;
         // ======== ffn V (rows of 4E bytes, four warps per row) + residual (rwkv.cu:574-577) =========
-        gather_quantise(sm.planes, sm.scal, vecp(q - 1), acc_buf(p, phase - 1), 1, 4 * E, ctid, gb, gn, p.trace);
+        gather_quantise(sm.planes, sm.scal, vecp(q - 1), acc_buf(p, phase - 1), 1, 4 * E, ctid, gb, gn, c_trace);
         stamp();
         rp = consume_sub<CPL, FULL, 4>(c_ring, c_full, c_empty, c_tile, c_stages, c_planes + (uint32_t)(0), c_res + (uint32_t)(0) * 8u, 4 * E, sl.e1 - sl.e0, rp, c_warp, c_lane, c_ptrace, c_tcnt);
         // issued after the register-hungry core; the loads land during the epilogue + grid barrier
@@ -928,7 +935,7 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
     grid_sync(p, phase, ctid);
     stamp();
     ++q;
-    gather_quantise(sm.planes, sm.scal, vecp(q - 1), acc_buf(p, phase - 1), 1, E, ctid, gb, gn, p.trace);
+    gather_quantise(sm.planes, sm.scal, vecp(q - 1), acc_buf(p, phase - 1), 1, E, ctid, gb, gn, c_trace);
     stamp();
     rp = consume_sub<CPL, FULL, 1>(c_ring, c_full, c_empty, c_tile, c_stages, c_planes + (uint32_t)(0), c_res + (uint32_t)(0) * 8u, E, sl.v1 - sl.v0, rp, c_warp, c_lane, c_ptrace, c_tcnt);
     tok_sync();

@@ -56,16 +56,14 @@ print("barrier release latency after LAST arrival (us): mean %.2f median %.2f" %
 tt = eng.read_tile_trace().astype(np.int64)
 n_cta = 148
 for cta in (0, 77):
-    issue, ready, cyc = tt[0, cta], tt[1, cta], tt[2, cta]
+    issue, ready = tt[0, cta], tt[1, cta]
     n_t = int((issue > 0).sum())
     issue, ready = (issue[:n_t] - t0) / 1e3, (ready[:n_t] - t0) / 1e3
-    wait = (cyc[:n_t] >> 40).astype(np.float64)
-    clk = (cyc[:n_t] & ((1 << 40) - 1)).astype(np.float64)
-    print("CTA %d: tiles %d; warp-0 wait cycles total %.0f of %.0f token cycles" % (cta, n_t, wait.sum(), clk[-1] - clk[0]))
+    print("CTA %d: tiles %d" % (cta, n_t))
     per_layer = 48 if workload == "7b" else None
     if per_layer:
         base = 2 * per_layer
-        print("layer-2 tiles of CTA %d: idx issue(us) got(us) lead(us) wait(cyc) dclk(cyc since previous tile)" % cta)
+        print("layer-2 tiles of CTA %d: idx issue(us) started(us) lead(us)" % cta)
         for i in range(base, min(base + per_layer, n_t)):
-            print("%4d %9.2f %9.2f %7.2f %7.0f %7.0f" % (i - base, issue[i], ready[i], ready[i] - issue[i], wait[i], clk[i] - clk[i - 1]))
+            print("%4d %9.2f %9.2f %7.2f" % (i - base, issue[i], ready[i], ready[i] - issue[i]))
 print("layer-2 stamps (CTA 0, us):", np.round(tr[0, 3 + 2 * 32:3 + 3 * 32] / 1e3, 2))
