@@ -137,7 +137,7 @@ def run_reference(args, pkg, workload):
                        "l2": "weights >> L2, every token streams from HBM"}}
     if not os.path.exists(REF_HARNESS):
         base["unavailable"] = "oracle/_ref/ref_harness not built (needs /root/reference at build time)"
-        print(json.dumps(base))
+        emit(base)
         return
     path = model_path(workload, pkg)
     tf = path + ".seed.txt"
@@ -156,7 +156,7 @@ def run_reference(args, pkg, workload):
             res = json.loads(line[len("REF_RESULT "):])
     if r.returncode != 0 or res is None:
         base["unavailable"] = "ref_harness failed rc=%d: %s" % (r.returncode, (r.stderr or r.stdout)[-300:].replace("\n", " "))
-        print(json.dumps(base))
+        emit(base)
         return
     toks = [int(x) for x in open(dump + ".tokens").read().split()][:6]
     cb = cpu_baseline(path, toks or [SEED_TOKEN] * 3, budget_s=20.0)
@@ -170,7 +170,7 @@ def run_reference(args, pkg, workload):
             os.remove(p)
         except OSError:
             pass
-    print(json.dumps(base))
+    emit(base)
 
 
 def ncu_traffic(kernel, workload):
@@ -187,7 +187,30 @@ def ncu_traffic(kernel, workload):
     return None
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE JSON line: point fd 1 at stderr for everything libraries print (NCCL's version
+    banner ignores NCCL_DEBUG_FILE) and keep the real stdout for emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    data = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=256)
@@ -220,8 +243,6 @@ def main():
     if world > 1:
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
-        # stdout carries ONE JSON line: NCCL's version banner / debug lines go to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     L, E = SHAPES[workload]
@@ -372,7 +393,7 @@ def main():
     }
     if alt is not None:
         out["alt"] = alt
-    print(json.dumps(out))
+    emit(out)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

@@ -840,6 +840,10 @@ int rwkv_b200_set_option(rwkv_b200_model *m, const char *key, const char *value)
         configure_mode(m);
     }
     else if (k == "max_layers") m->max_layers = v;
+    else if (k == "issue_gap") {
+        if (v < 0 || v > 100000) return fail(1, "issue_gap is a cycle count in 0..100000");
+        m->p.issue_gap = v;
+    }
     else if (k == "stages") {
         if (v < 2 || v > rk::kMaxStages) return fail(1, "stages must be 2..%d", rk::kMaxStages);
         const size_t smem = rk::smem_bytes(v, m->p.tile_bytes, m->p.plane_cap);

@@ -82,6 +82,7 @@ struct Params {
     Ctrl *ctrl;
     // ---- persistent token kernel (k_token) ------------------------------------------------
     int L_run;                         // layers to run (debug knob; normally == L)
+    int issue_gap;                     // minimum SM cycles between two bulk-copy issues of the producer (0 = unpaced)
     int feed_mode;                     // 0: ctrl->token, 1: ctrl->next (free-running), 2: stream[ctrl->pos]
     int greedy;                        // 1: finish with an on-device argmax into ctrl->next
     const unsigned long long *stream;  // device-resident token stream (feed_mode 2)

@@ -59,7 +59,10 @@ for cta in (0, 77):
     issue, ready = tt[0, cta], tt[1, cta]
     n_t = int((issue > 0).sum())
     issue, ready = (issue[:n_t] - t0) / 1e3, (ready[:n_t] - t0) / 1e3
-    print("CTA %d: tiles %d" % (cta, n_t))
+    d_t = np.diff(ready)
+    inside = d_t[d_t < 2.0]  # consecutive tiles of one streaming phase (gaps are phase boundaries)
+    print("CTA %d: tiles %d; tile period inside a phase (us): median %.3f mean %.3f p90 %.3f" % (
+        cta, n_t, np.median(inside), inside.mean(), np.percentile(inside, 90)))
     per_layer = 48 if workload == "7b" else None
     if per_layer:
         base = 2 * per_layer
