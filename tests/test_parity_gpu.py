@@ -81,6 +81,22 @@ def test_169m_storygen_length(pkg, make_model):
     print("169M worst rel err %.3g, argmax checked %d" % (worst, n))
 
 
+def test_1b5_full_depth(pkg, make_model):
+    """BASELINE config: RWKV-4 1.5B shape at full depth (24 x 2048)."""
+    worst, n = run_pair(pkg, make_model(24, 2048), 6)
+    print("1.5B worst rel err %.3g, argmax checked %d" % (worst, n))
+
+
+def test_7b_full_size_bench_model(pkg):
+    """The headline workload itself (32 x 4096, the file bench.py streams): three tokens against the oracle."""
+    import sys
+    from util import ROOT
+    sys.path.insert(0, ROOT)
+    import bench
+    worst, n = run_pair(pkg, bench.model_path("7b", pkg), 3)
+    print("7B worst rel err %.3g, argmax checked %d" % (worst, n))
+
+
 def test_graph_and_eager_agree_bitwise(pkg, make_model):
     """The CUDA-graph replay and launch-by-launch execution must be the same computation."""
     path = make_model(2, 2048)
