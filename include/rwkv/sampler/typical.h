@@ -34,31 +34,45 @@ inline std::mt19937_64 &rwkv_sampler_generator() {
     return gen;
 }
 
+// The draw itself restates what std::discrete_distribution<int>(probs)(gen) computes in libstdc++
+// (bits/random.tcc: param_type::_M_initialize and operator()) without its two 400 KB vectors:
+//   s = accumulate(probs); q_i = probs_i / s; cp_i = q_0 + ... + q_i (sequential), cp_last = 1.0;
+//   u = generate_canonical<double, 53>(gen);  token = first i with cp_i >= u   (lower_bound).
+// Same operations in the same order on the same doubles, hence the same tokens; tests/test_sampler.py
+// checks the sequences against the ones drawn by the reference binary.
+inline int rwkv_sampler_draw(const double *probs, int len, std::mt19937_64 &gen) {
+    double s = 0.0;
+    for (int i = 0; i < len; ++i) s += probs[i];
+    const double u = std::generate_canonical<double, 53>(gen);
+    double c = 0.0;
+    for (int i = 0; i + 1 < len; ++i) {
+        c += probs[i] / s;
+        if (!(c < u)) return i;
+    }
+    return len - 1; // cp_last is forced to 1.0 and u < 1
+}
+
 inline int typical(float *_logits, float _temp = 0.9, float _tau = 0.8) {
     constexpr int len = 50277;
     (void)_tau; // see the header comment: the reference's cutoff never reaches `probs`
-    std::vector<double> probs(len);
+    static thread_local std::vector<double> probs(len);
     double total = 0.0;
     for (int i = 0; i < len; ++i) {
         probs[i] = std::exp((double)_logits[i]);
         total += probs[i];
     }
-    for (int i = 0; i < len; ++i) probs[i] /= total;
-
-    if (_temp != 1.0) {
-        const uint8_t exponent = (uint8_t)(1.0 / _temp);
+    const uint8_t exponent = _temp != 1.0 ? (uint8_t)(1.0 / _temp) : (uint8_t)1;
+    if (exponent == 0) {
+        for (int i = 0; i < len; ++i) probs[i] = 1.0;
+    } else {
         for (int i = 0; i < len; ++i) {
-            if (exponent == 0) {
-                probs[i] = 1.0;
-                continue;
-            }
-            double v = probs[i];
-            for (uint8_t e = 1; e < exponent; ++e) v *= probs[i];
+            const double q = probs[i] / total;
+            double v = q;
+            for (uint8_t e = 1; e < exponent; ++e) v *= q;
             probs[i] = v;
         }
     }
-    std::discrete_distribution<int> dist(probs.begin(), probs.end());
-    return dist(rwkv_sampler_generator());
+    return rwkv_sampler_draw(probs.data(), len, rwkv_sampler_generator());
 }
 
 // Locally typical sampling as the reference's header comment (typical.h:1-18) specifies it:
