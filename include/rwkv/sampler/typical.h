@@ -39,11 +39,11 @@ inline std::mt19937_64 &rwkv_sampler_generator() {
 //   s = accumulate(probs); q_i = probs_i / s; cp_i = q_0 + ... + q_i (sequential), cp_last = 1.0;
 //   u = generate_canonical<double, 53>(gen);  token = first i with cp_i >= u   (lower_bound).
 // Same operations in the same order on the same doubles, hence the same tokens; tests/test_sampler.py
-// checks the sequences against the ones drawn by the reference binary.
-inline int rwkv_sampler_draw(const double *probs, int len, std::mt19937_64 &gen) {
+// checks the sequences against the ones drawn by the reference binary. (The uniform is drawn after the
+// probabilities are built, as the reference does; it is the generator's only consumer.)
+inline int rwkv_sampler_pick(const double *probs, int len, double u) {
     double s = 0.0;
     for (int i = 0; i < len; ++i) s += probs[i];
-    const double u = std::generate_canonical<double, 53>(gen);
     double c = 0.0;
     for (int i = 0; i + 1 < len; ++i) {
         c += probs[i] / s;
@@ -52,9 +52,9 @@ inline int rwkv_sampler_draw(const double *probs, int len, std::mt19937_64 &gen)
     return len - 1; // cp_last is forced to 1.0 and u < 1
 }
 
-inline int typical(float *_logits, float _temp = 0.9, float _tau = 0.8) {
+// probs = exp(l) / sum(exp(l)), then ^ uint8(1/temp): the distribution `typical()` samples from
+inline const std::vector<double> &rwkv_sampler_probs(const float *_logits, float _temp) {
     constexpr int len = 50277;
-    (void)_tau; // see the header comment: the reference's cutoff never reaches `probs`
     static thread_local std::vector<double> probs(len);
     double total = 0.0;
     for (int i = 0; i < len; ++i) {
@@ -72,7 +72,21 @@ inline int typical(float *_logits, float _temp = 0.9, float _tau = 0.8) {
             probs[i] = v;
         }
     }
-    return rwkv_sampler_draw(probs.data(), len, rwkv_sampler_generator());
+    return probs;
+}
+
+// typical() with the uniform supplied by the caller (RWKV::sample uses it when the device sampler's
+// answer is too close to an interval boundary to be trusted)
+inline int typical_with_u(const float *_logits, float _temp, double u) {
+    const std::vector<double> &probs = rwkv_sampler_probs(_logits, _temp);
+    return rwkv_sampler_pick(probs.data(), (int)probs.size(), u);
+}
+
+inline int typical(float *_logits, float _temp = 0.9, float _tau = 0.8) {
+    (void)_tau; // see the header comment: the reference's cutoff never reaches `probs`
+    const std::vector<double> &probs = rwkv_sampler_probs(_logits, _temp);
+    const double u = std::generate_canonical<double, 53>(rwkv_sampler_generator());
+    return rwkv_sampler_pick(probs.data(), (int)probs.size(), u);
 }
 
 // Locally typical sampling as the reference's header comment (typical.h:1-18) specifies it:

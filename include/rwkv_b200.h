@@ -149,6 +149,16 @@ int rwkv_b200_profile(rwkv_b200_model *m, const unsigned long long *tokens,
 /* Kernel launches issued by this model since load (for bench.py "gpu_launches"). */
 unsigned long long rwkv_b200_launch_count(const rwkv_b200_model *m);
 
+/* Device-side restatement of `typical(logits, temp, tau)` (R sampler/typical.h:20-58 as it actually
+ * behaves, see include/rwkv/sampler/typical.h) on the logits of the LAST forward, which never leave
+ * the GPU: probs = exp(l)/sum, probs ^ uint8(1/temp), cumulative sums, first index whose cumulative
+ * probability reaches `u`, the uniform in [0,1) the caller drew from its generator
+ * (std::generate_canonical<double,53> keeps the reference's random stream). `*margin` is the distance
+ * of `u` to the nearest interval boundary; device sums are block reductions, so a caller that wants
+ * the host's token in every case re-samples on the host when margin < 1e-9 (RWKV::sample does). */
+int rwkv_b200_sample_typical(rwkv_b200_model *m, float temp, double u, unsigned long long *token,
+                             double *margin);
+
 /* Engine knobs (all optional): key/value strings, e.g. ("graph","0"), ("pdl","1").
  * Returns non-zero for an unknown key. */
 int rwkv_b200_set_option(rwkv_b200_model *m, const char *key, const char *value);

@@ -74,8 +74,10 @@ static py::object tokenizerDecode(void *h, int token) {
     return py::reinterpret_steal<py::object>(u);
 }
 
+// Samples from the logits of the last modelForward. The Python side never gets a writable view of the
+// internal logits (getOutput copies), so the device sampler gives exactly the host sampler's tokens here.
 static int typicalSample(void *h, float temp = 0.9, float tau = 0.8) {
-    return typical(static_cast<RWKV *>(h)->out, temp, tau);
+    return static_cast<RWKV *>(h)->sample(temp, tau);
 }
 
 static std::tuple<int64_t, int64_t> loadWrapper(void *h, const std::string &filename) {

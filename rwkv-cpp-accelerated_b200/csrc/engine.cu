@@ -62,6 +62,7 @@ struct rwkv_b200_model {
     int sms = 0;
     int grid = 0;
     int cpl = 0;
+    double *d_sample = nullptr, *h_sample = nullptr; // device sampler result {token, margin}
     size_t xch_bytes = 0;   // exchange block (peer-visible with tensor parallelism)
     bool tp_wired = false;  // peers' exchange blocks imported
     std::vector<void *> ipc_opened;
@@ -574,6 +575,7 @@ void rwkv_b200_free(rwkv_b200_model *m) {
     if (m->h_ctrl) cudaFreeHost(m->h_ctrl);
     if (m->h_logits) cudaFreeHost(m->h_logits);
     if (m->h_next) cudaFreeHost(m->h_next);
+    if (m->h_sample) cudaFreeHost(m->h_sample);
     if (m->stream) cudaStreamDestroy(m->stream);
     delete m;
 }
@@ -696,6 +698,27 @@ int rwkv_b200_forward_greedy(rwkv_b200_model *m, unsigned long long token, unsig
 }
 
 float *rwkv_b200_logits_host(rwkv_b200_model *m) { return m ? m->h_logits : nullptr; }
+
+int rwkv_b200_sample_typical(rwkv_b200_model *m, float temp, double u, unsigned long long *token, double *margin) {
+    int rc = check_model(m);
+    if (rc) return rc;
+    if (!token) return fail(1, "null argument");
+    CK(cudaSetDevice(m->device));
+    if (!m->d_sample) {
+        if ((rc = dmalloc(m, &m->d_sample, 2))) return rc;
+        CK(cudaMallocHost((void **)&m->h_sample, 2 * sizeof(double)));
+    }
+    // the reference applies the temperature as probs ^ uint8(1 / temp) (include/rwkv/sampler/typical.h)
+    const int exponent = temp != 1.0f ? (int)(unsigned char)(1.0 / (double)temp) : 1;
+    rk::k_sample_typical<<<1, rk::kSampleThreads, 0, m->stream>>>(m->p.logits, (int)binfmt::kVocab, exponent, u, m->d_sample);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(m->h_sample, m->d_sample, 2 * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+    CK(cudaStreamSynchronize(m->stream));
+    *token = (unsigned long long)m->h_sample[0];
+    if (margin) *margin = m->h_sample[1];
+    m->launches += 1;
+    return 0;
+}
 
 int rwkv_b200_decode_timed(rwkv_b200_model *m, const unsigned long long *tokens, unsigned long long n,
                            int teacher_forced, float *ms) {

@@ -55,6 +55,7 @@ def load_library():
         "rwkv_b200_forward": (i32, [vp, pull, ull, i32, pflt]),
         "rwkv_b200_forward_greedy": (i32, [vp, ull, pull, pflt]),
         "rwkv_b200_logits_host": (pflt, [vp]),
+        "rwkv_b200_sample_typical": (i32, [vp, c.c_float, c.c_double, pull, pdbl]),
         "rwkv_b200_debug_read": (c.c_longlong, [vp, cp, vp, c.c_size_t]),
         "rwkv_b200_decode_timed": (i32, [vp, pull, ull, i32, pflt]),
         "rwkv_b200_kernel_count": (i32, []),
@@ -139,6 +140,12 @@ class Engine:
         self._ck(self.lib.rwkv_b200_forward(self.h, _ptr(toks, ctypes.c_ulonglong), len(toks), mode,
                                             _ptr(out, ctypes.c_float)), "forward")
         return out
+
+    def sample_typical(self, temp, u):
+        """Device sampler on the logits of the last forward: (token, margin) for the uniform `u`."""
+        tok, margin = ctypes.c_ulonglong(), ctypes.c_double()
+        self._ck(self.lib.rwkv_b200_sample_typical(self.h, temp, u, ctypes.byref(tok), ctypes.byref(margin)), "sample_typical")
+        return int(tok.value), float(margin.value)
 
     def forward_greedy(self, token, want_logits=False):
         nxt = ctypes.c_ulonglong()
