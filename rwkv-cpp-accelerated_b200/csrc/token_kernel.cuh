@@ -754,7 +754,6 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
         gather_quantise(sm.planes, sm.scal, vecp(q - 1), acc_buf(p, phase - 1), 3, E, ctid, gb, gn, c_trace);
         stamp();
         {
-#ifndef RK_EXP1
             double aa = 0, bb = 0, wd = 0, ub = 0, ewd = 0;
             float ro = 0, oco = 0;
             if (mine) {
@@ -766,25 +765,11 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
                 ro = p.ro[lo + j];
                 oco = p.oco[lo + j];
             }
-#endif
             const size_t mo = (size_t)lq * E * E;
             (void)mo;
             rp = consume_sub<CPL, FULL, 1>(c_ring, c_full, c_empty, c_tile, c_stages, c_planes + (uint32_t)(0), c_res + (uint32_t)(0) * 8u, E, sl.e1 - sl.e0, rp, c_warp, c_lane, c_ptrace, c_tcnt);
             rp = consume_sub<CPL, FULL, 1>(c_ring, c_full, c_empty, c_tile, c_stages, c_planes + (uint32_t)(3 * E), c_res + (uint32_t)(ne * 1) * 8u, E, sl.e1 - sl.e0, rp, c_warp, c_lane, c_ptrace, c_tcnt);
             rp = consume_sub<CPL, FULL, 1>(c_ring, c_full, c_empty, c_tile, c_stages, c_planes + (uint32_t)(6 * E), c_res + (uint32_t)(2 * ne * 1) * 8u, E, sl.e1 - sl.e0, rp, c_warp, c_lane, c_ptrace, c_tcnt);
-#ifdef RK_EXP1
-            double aa = 0, bb = 0, wd = 0, ub = 0, ewd = 0;
-            float ro = 0, oco = 0;
-            if (mine) {
-                aa = p.saa[so + lo + j];
-                bb = p.sbb[so + lo + j];
-                wd = p.decay[lo + j];
-                ub = p.bonus[lo + j];
-                ewd = p.expdecay[lo + j];
-                ro = p.ro[lo + j];
-                oco = p.oco[lo + j];
-            }
-#endif
             tok_sync();
             stamp();
             double mx[3] = {0, 0, 0}, of[3] = {0, 0, 0};
