@@ -996,33 +996,6 @@ __global__ void __launch_bounds__(256) k_transpose_xor(const uint8_t *__restrict
     }
 }
 
-// Load-time repack into the token kernel's "lane = row" layout (see token_kernel.cuh):
-// raw u8 [N in][M out] (leading dim ld_raw) -> s8 (value ^ 0x80); row k of the grid's CTA b lives at
-//   r0(b)*N + 32*g*N + (c*gr + lane)*16 + byte,   g = (k-r0)/32, lane = (k-r0)%32, gr = rows in that group.
-// One thread per (row k, 16-byte chunk c); consecutive threads take consecutive rows, so both the
-// byte gathers from `raw` and the 16-byte stores are coalesced.
-__global__ void __launch_bounds__(256) k_repack_lane(const uint8_t *__restrict__ raw, size_t ld_raw, int M, int N, int G,
-                                                     int8_t *__restrict__ out) {
-    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int nc = N >> 4;
-    if (tid >= (long long)M * nc) return;
-    const int k = (int)(tid % M), c = (int)(tid / M);
-    int b = (int)(((long long)k * G) / M); // owner CTA: r0(b) <= k < r0(b+1), r0(b) = M*b/G
-    while ((int)(((long long)M * (b + 1)) / G) <= k) ++b;
-    while ((int)(((long long)M * b) / G) > k) --b;
-    const int r0 = (int)(((long long)M * b) / G), r1 = (int)(((long long)M * (b + 1)) / G);
-    const int g = (k - r0) >> 5, lane = (k - r0) & 31;
-    const int gr = min(32, (r1 - r0) - 32 * g);
-    uint32_t w[4] = {0, 0, 0, 0};
-#pragma unroll
-    for (int e = 0; e < 16; ++e) {
-        const uint32_t v = (uint32_t)(raw[(size_t)(16 * c + e) * ld_raw + k] ^ 0x80u);
-        w[e >> 2] |= v << (8 * (e & 3));
-    }
-    const size_t off = (size_t)r0 * N + (size_t)32 * g * N + ((size_t)c * gr + lane) * 16;
-    *reinterpret_cast<uint4 *>(out + off) = make_uint4(w[0], w[1], w[2], w[3]);
-}
-
 __global__ void k_exp_table(const double *__restrict__ in, double *__restrict__ out, size_t n) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = exp(in[i]);
