@@ -47,6 +47,11 @@ def algorithmic_bytes_per_token(L, E):
     return w + 4 * (20 * L * E + 2 * E) + 8 * (7 * L * E + 4 * (L + 1) * E) + 64 * L * E + 4 * E + 4 * VOCAB
 
 
+def metric_name(workload):
+    """BASELINE.json's metric; both arms print the identical string so that the driver can divide them."""
+    return "tokens/sec single-stream decode RWKV-4 %s uint8; achieved HBM GB/s vs peak" % {"7b": "7B", "14b": "14B", "1b5": "1.5B", "169m": "169M"}[workload]
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -130,7 +135,7 @@ def run_reference(args, pkg, workload):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    base = {"impl": "reference", "metric": "tokens/sec single-stream decode", "unit": "tokens/s", "n_gpus": args.gpus,
+    base = {"impl": "reference", "metric": metric_name(workload), "unit": "tokens/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8 weights, f32/f64 math", "data": "synthetic",
             "config": {"workload": "RWKV-4 %s shape L=%d E=%d uint8, random-init, greedy single-stream decode" % (workload, L, E),
@@ -162,7 +167,10 @@ def run_reference(args, pkg, workload):
     cb = cpu_baseline(path, toks or [SEED_TOKEN] * 3, budget_s=20.0)
     v = res["tokens_per_s"]
     base.update({"value": v, "ms_per_step": 1000.0 / v if v else None, "clocks": clocks,
-                 "e2e": {"value": v, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                 # the reference's forward copies the embedding row and the five state arrays up and the logits
+                 # and the five state arrays down on every token (rwkv.h:353,372; rwkv.cu:467-490, 513-515)
+                 "e2e": {"value": v, "unit": "tokens/s", "h2d_bytes_per_step": 4 * E + 5 * L * E * 8,
+                         "d2h_bytes_per_step": 4 * VOCAB + 5 * L * E * 8},
                  "cpu_baseline": cb, "gpu_launches": (9 + 20 * L) * args.steps,
                  "reference_arm": "unmodified /root/reference rwkv.cu + rwkv.h on 1 GPU (its own RWKV::forward incl. its host<->device state copies)"})
     for p in (dump, dump + ".tokens", tf):
@@ -385,8 +393,7 @@ def main():
     eng.close()
 
     out = {
-        "metric": "tokens/sec single-stream decode RWKV-4 7B uint8; achieved HBM GB/s vs peak" if workload == "7b"
-        else "tokens/sec single-stream decode RWKV-4 %s uint8; achieved HBM GB/s vs peak" % workload,
+        "metric": metric_name(workload),
         "value": round(value, 2), "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms / args.steps, 5), "higher_is_better": True, "scaling": "strong" if tp else "weak", "vs_baseline": None,
         "dtype": "u8 weights x 23-bit fixed-point activations (byte limbs u8,u8,s8; exact int32 dp4a accumulate), f64 elementwise",
