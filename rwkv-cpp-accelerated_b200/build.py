@@ -50,7 +50,7 @@ def nvcc():
 
 
 def build_engine(force=False):
-    srcs = [os.path.join(CSRC, f) for f in ("engine.cu", "kernels.cuh", "token_kernel.cuh", "binfmt.h")]
+    srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))]
     srcs.append(os.path.join(ROOT, "include", "rwkv_b200.h"))
     if force or _newer(LIB, srcs):
         _run([nvcc()] + NVCC_FLAGS + ["-o", LIB, os.path.join(CSRC, "engine.cu")])

@@ -1,15 +1,17 @@
 // engine.cu — host side of the B200 RWKV-v4 uint8 decode engine + the C ABI (include/rwkv_b200.h).
 //
 // Responsibilities:
-//   * load a reference-format .bin (include/rwkv/cuda/rwkv.cu:638-717 semantics), stage it
-//     through pinned memory, and repack on the device (transpose to [out][in], centre to s8,
-//     fold 128*r + o into one offset vector);
+//   * load a reference-format .bin (include/rwkv/cuda/rwkv.cu:638-717 semantics): each rank reads only
+//     the slices of the matrices it streams, stages them through pinned memory, and repacks on the device
+//     (transpose to [out][in], centre to s8, fold 128*r + o into one offset vector);
 //   * keep state, embedding table, weights and logits resident in HBM;
-//   * issue one token as 2 + 4*L kernels, normally replayed as a single CUDA graph;
-//   * measurement hooks used by bench.py (device-timed decode, per-kernel event profile).
+//   * issue one token as ONE cooperative launch of the persistent token kernel (token_kernel.cuh);
+//   * wire the exchange blocks of the ranks of a tensor-parallel group (CUDA IPC);
+//   * measurement hooks used by bench.py.
 //
-// There is deliberately no CPU code path: every entry point that computes fails with an
-// error when no sm_100 device is present.
+// There is deliberately no CPU code path: every entry point that computes fails with an error when
+// no sm_100 device is present.
+#include <algorithm>
 #include <cerrno>
 #include <cstdarg>
 #include <cstdio>
@@ -26,8 +28,9 @@
 
 #include "../../include/rwkv/enums/enum.h"
 #include "../../include/rwkv_b200.h"
+#include "aux_kernels.cuh"
 #include "binfmt.h"
-#include "kernels.cuh"
+#include "prefill.cuh"
 #include "token_kernel.cuh"
 
 namespace {
@@ -52,8 +55,7 @@ int fail(int code, const char *fmt, ...) {
                         __FILE__, __LINE__);                                                       \
     } while (0)
 
-enum KernelClass { K_EMBED = 0, K_ATT_KVR, K_ATT_OUT, K_FFN_RK, K_FFN_V, K_HEAD, K_ARGMAX, K_TOKEN, K_COUNT };
-const char *kKernelNames[K_COUNT] = {"embed_ln0", "att_kvr", "att_out", "ffn_rk", "ffn_v", "head", "argmax", "token"};
+const char *kKernelNames[1] = {"token"};
 
 } // namespace
 
@@ -76,14 +78,12 @@ struct rwkv_b200_model {
     rk::Ctrl *h_ctrl = nullptr; // pinned [max_gpt]
     float *h_logits = nullptr;  // pinned [max_gpt][V]
     unsigned long long *h_next = nullptr;
-    // graphs
-    bool use_graph = true;
-    bool token_mode = true; // one persistent cooperative kernel per token (default) vs one kernel per phase
-    int max_layers = -1; // debug: run only the first n layers
-    cudaGraphExec_t g_plain = nullptr, g_greedy = nullptr, g_free = nullptr, g_stream = nullptr;
-    const unsigned long long *g_stream_src = nullptr;
+    rk::Diag *h_diag = nullptr; // mapped pinned: the kernel's last words before a timeout trap
+    int max_layers = -1;        // debug: run only the first n layers
     unsigned long long launches = 0;
+    unsigned int epoch = 0, tk = 0; // exchange epochs (token_kernel.cuh); identical on every rank
     int tp_rank = 0, tp_size = 1;
+    rk::PrefillState pf{};
 };
 
 namespace {
@@ -100,89 +100,53 @@ template <class T> int dmalloc(M *m, T **out, size_t count) {
 
 int layers_to_run(const M *m) { return m->max_layers >= 0 && m->max_layers < (int)m->L ? m->max_layers : (int)m->L; }
 
-unsigned long long kernels_per_token(const M *m, bool greedy) {
-    if (m->token_mode) return 1ull;
-    return 2ull + 4ull * layers_to_run(m) + (greedy ? 1 : 0);
+// A failed synchronisation: if the kernel left a diagnostic record, say what it was waiting for.
+int sync_failed(M *m, cudaError_t e, const char *what) {
+    const rk::Diag *d = m->h_diag;
+    if (d && d->code) {
+        static const char *names[] = {"", "slice statistics", "activation vector", "offset sums", "peer partial sums",
+                                      "sigmoid exchange", "completion flags", "arg-max candidates", "ring (full)", "ring (empty)"};
+        return fail(100 + (int)e,
+                    "%s failed: %s; token kernel timed out waiting for %s: rank %u cta %u thread %u layer %u kind %u "
+                    "expected tag %u saw %u aux %llu (a peer rank that never launched, or a protocol bug)",
+                    what, cudaGetErrorString(e), d->code < 10 ? names[d->code] : "?", d->rank, d->cta, d->thread, d->layer,
+                    d->kind, d->expect, d->seen, d->aux);
+    }
+    return fail(100 + (int)e, "%s failed: %s", what, cudaGetErrorString(e));
 }
+#define SYNC(m)                                                          \
+    do {                                                                 \
+        cudaError_t e__ = cudaStreamSynchronize((m)->stream);            \
+        if (e__ != cudaSuccess) return sync_failed((m), e__, "forward"); \
+    } while (0)
 
 // ---- kernel dispatch on the model width -------------------------------------------------
-template <int CPL> int set_attrs(size_t smem) {
-    CK(cudaFuncSetAttribute(rk::k_att_kvr<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CK(cudaFuncSetAttribute(rk::k_att_out<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CK(cudaFuncSetAttribute(rk::k_ffn_rk<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CK(cudaFuncSetAttribute(rk::k_ffn_v<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CK(cudaFuncSetAttribute(rk::k_head<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    return 0;
-}
-template <int CPL> int set_attrs_tok(size_t smem) {
-    CK(cudaFuncSetAttribute(rk::k_token<CPL, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CK(cudaFuncSetAttribute(rk::k_token<CPL, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CK(cudaFuncSetAttribute(rk::k_token<CPL, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CK(cudaFuncSetAttribute(rk::k_token<CPL, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    return 0;
-}
-template <int CPL> const void *token_entry(bool full, bool trace) {
-    if (trace) return full ? (const void *)rk::k_token<CPL, true, true> : (const void *)rk::k_token<CPL, false, true>;
-    return full ? (const void *)rk::k_token<CPL, true, false> : (const void *)rk::k_token<CPL, false, false>;
-}
+// CPL = 16-byte chunks per lane of an n_embed-byte row; FULL = n_embed == CPL * 512 (no tail predicates).
+#define RK_CPLS(X) X(2) X(4) X(6) X(8) X(10)
 
-struct EventPair {
-    cudaEvent_t a, b;
-};
-
-// Optional per-launch timing (profile mode): records an event pair around each launch.
-struct Prof {
-    std::vector<std::pair<int, EventPair>> ev;
-};
-
-template <int CPL> int launch_class(M *m, int cls, int layer, cudaStream_t s) {
-    const dim3 g(m->grid), b(rk::kThreads);
-    switch (cls) {
-    case K_ATT_KVR: rk::k_att_kvr<CPL><<<g, b, m->smem, s>>>(m->p, layer); break;
-    case K_ATT_OUT: rk::k_att_out<CPL><<<g, b, m->smem, s>>>(m->p, layer); break;
-    case K_FFN_RK: rk::k_ffn_rk<CPL><<<g, b, m->smem, s>>>(m->p, layer); break;
-    case K_FFN_V: rk::k_ffn_v<CPL><<<g, b, m->smem, s>>>(m->p, layer); break;
-    case K_HEAD: rk::k_head<CPL><<<g, b, m->smem, s>>>(m->p); break;
-    default: return fail(3, "bad kernel class %d", cls);
+const void *token_entry(int cpl, bool full, bool trace) {
+#define X(A)                                                                                                          \
+    if (cpl == A) {                                                                                                   \
+        if (trace) return full ? (const void *)rk::k_token<A, true, true> : (const void *)rk::k_token<A, false, true>; \
+        return full ? (const void *)rk::k_token<A, true, false> : (const void *)rk::k_token<A, false, false>;          \
     }
-    return 0;
+    RK_CPLS(X)
+#undef X
+    return nullptr;
 }
 
-int launch_one(M *m, int cls, int layer, cudaStream_t s, Prof *prof) {
-    EventPair ep{};
-    if (prof) {
-        CK(cudaEventCreate(&ep.a));
-        CK(cudaEventCreate(&ep.b));
-        CK(cudaEventRecord(ep.a, s));
-    }
-    int rc = 0;
-    if (cls == K_EMBED) rk::k_embed_ln0<<<1, rk::kConsumers, 0, s>>>(m->p);
-    else if (cls == K_ARGMAX) rk::k_argmax<<<1, 1024, 0, s>>>(m->p);
-    else {
-        switch (m->cpl) {
-        case 2: rc = launch_class<2>(m, cls, layer, s); break;
-        case 4: rc = launch_class<4>(m, cls, layer, s); break;
-        case 8: rc = launch_class<8>(m, cls, layer, s); break;
-        case 10: rc = launch_class<10>(m, cls, layer, s); break;
-        default: rc = fail(3, "unsupported chunks-per-lane %d", m->cpl);
-        }
-    }
-    if (rc) return rc;
-    CK(cudaGetLastError());
-    if (prof) {
-        CK(cudaEventRecord(ep.b, s));
-        prof->ev.push_back({cls, ep});
-    }
-    return 0;
+int chunks_per_lane(unsigned long long seg_bytes) {
+    int c = (int)((seg_bytes + 511) / 512);
+    if (c < 2) c = 2;
+    return (c + 1) & ~1;
 }
 
-// Ring geometry per mode. Token kernel: a tile is eight row segments of n_embed bytes (one per
-// consumer warp); staged kernels: 20 KB tiles. As many stages as fit beside the limb planes.
-void configure_mode(M *m) {
+// Ring geometry: a tile is eight row segments of n_embed bytes (one per consumer warp); as many stages
+// as fit beside the limb planes.
+void configure_ring(M *m) {
     rk::Params &p = m->p;
-    p.tile_bytes = m->token_mode ? (int)(8 * m->E) : 20480;
-    if (p.tile_bytes < (int)(4 * m->E)) p.tile_bytes = (int)(4 * m->E);
-    p.stages = (int)std::min<size_t>(rk::kMaxStages, (232448 - rk::smem_bytes(0, 0, p.plane_cap)) / p.tile_bytes);
+    p.tile_bytes = (int)(8 * m->E);
+    p.stages = (int)std::min<size_t>(rk::kMaxStages, (rk::kSmemLimit - rk::smem_bytes(0, 0, p.plane_cap)) / p.tile_bytes);
     m->smem = rk::smem_bytes(p.stages, p.tile_bytes, p.plane_cap);
 }
 
@@ -194,76 +158,16 @@ int launch_token(M *m, int feed, bool greedy, const unsigned long long *stream, 
     prm.feed_mode = feed;
     prm.greedy = greedy ? 1 : 0;
     prm.stream = stream;
+    prm.ep0 = m->epoch;
+    prm.tk = ++m->tk;
+    if (prm.tk == 0) prm.tk = ++m->tk; // tag 0 means "never written"
+    m->epoch += (unsigned int)prm.L_run + 1u;
     void *args[] = {&prm};
     const bool full = m->E == (unsigned long long)m->cpl * 512ull;
-    const bool trace = m->p.trace != nullptr;
-    const void *fn = m->cpl == 2 ? token_entry<2>(full, trace) : m->cpl == 4 ? token_entry<4>(full, trace)
-                   : m->cpl == 8 ? token_entry<8>(full, trace) : token_entry<10>(full, trace);
-    CK(cudaLaunchCooperativeKernel(fn, dim3(m->grid), dim3(rk::kTokThreads), args, m->smem, s));
-    return 0;
-}
-
-// The kernel sequence of one token.
-int enqueue_token(M *m, cudaStream_t s, bool greedy, Prof *prof) {
-    int rc;
-    if ((rc = launch_one(m, K_EMBED, 0, s, prof))) return rc;
-    const int nl = layers_to_run(m);
-    for (int l = 0; l < nl; ++l) {
-        if ((rc = launch_one(m, K_ATT_KVR, l, s, prof))) return rc;
-        if ((rc = launch_one(m, K_ATT_OUT, l, s, prof))) return rc;
-        if ((rc = launch_one(m, K_FFN_RK, l, s, prof))) return rc;
-        if ((rc = launch_one(m, K_FFN_V, l, s, prof))) return rc;
-    }
-    if ((rc = launch_one(m, K_HEAD, 0, s, prof))) return rc;
-    if (greedy && (rc = launch_one(m, K_ARGMAX, 0, s, prof))) return rc;
-    return 0;
-}
-
-enum GraphKind { G_PLAIN, G_GREEDY, G_FREE, G_STREAM };
-
-int build_graph(M *m, GraphKind kind, const unsigned long long *stream_src, cudaGraphExec_t *out) {
-    cudaGraph_t g = nullptr;
-    CK(cudaStreamBeginCapture(m->stream, cudaStreamCaptureModeThreadLocal));
-    int rc = 0;
-    if (kind == G_FREE) rk::k_feed_next<<<1, 32, 0, m->stream>>>(m->p);
-    if (kind == G_STREAM) rk::k_feed_stream<<<1, 32, 0, m->stream>>>(m->p, stream_src);
-    rc = enqueue_token(m, m->stream, kind == G_GREEDY || kind == G_FREE, nullptr);
-    cudaError_t e = cudaStreamEndCapture(m->stream, &g);
-    if (rc) {
-        if (g) cudaGraphDestroy(g);
-        return rc;
-    }
-    if (e != cudaSuccess) return fail(100 + (int)e, "cudaStreamEndCapture failed: %s", cudaGetErrorString(e));
-    e = cudaGraphInstantiate(out, g, 0);
-    cudaGraphDestroy(g);
-    if (e != cudaSuccess) return fail(100 + (int)e, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
-    return 0;
-}
-
-void drop_graphs(M *m) {
-    for (cudaGraphExec_t *g : {&m->g_plain, &m->g_greedy, &m->g_free, &m->g_stream}) {
-        if (*g) cudaGraphExecDestroy(*g);
-        *g = nullptr;
-    }
-    m->g_stream_src = nullptr;
-}
-
-int run_token(M *m, bool greedy) {
-    if (m->token_mode) {
-        int rc = launch_token(m, 0, greedy, nullptr, m->stream);
-        if (rc) return rc;
-    } else if (!m->use_graph) {
-        int rc = enqueue_token(m, m->stream, greedy, nullptr);
-        if (rc) return rc;
-    } else {
-        cudaGraphExec_t *g = greedy ? &m->g_greedy : &m->g_plain;
-        if (!*g) {
-            int rc = build_graph(m, greedy ? G_GREEDY : G_PLAIN, nullptr, g);
-            if (rc) return rc;
-        }
-        CK(cudaGraphLaunch(*g, m->stream));
-    }
-    m->launches += kernels_per_token(m, greedy);
+    const void *fn = token_entry(m->cpl, full, m->p.trace != nullptr);
+    if (!fn) return fail(3, "no kernel for %d chunks per lane", m->cpl);
+    CK(cudaLaunchCooperativeKernel(fn, dim3(m->grid), dim3(rk::kThreads), args, m->smem, s));
+    m->launches += 1;
     return 0;
 }
 
@@ -294,18 +198,21 @@ int read_exact(int fd, void *dst, size_t n, uint64_t off) {
     return 0;
 }
 
-// file[off, off+n) -> device dst, through the pinned staging buffer.
-int upload(M *m, FileReader &fr, uint64_t off, size_t n, void *dst) {
+// `rows` file rows of `row_stride` bytes starting at `off`; of each row the bytes [col0, col0 + cols)
+// -> device dst, packed [rows][cols], through the pinned staging buffer. A rank of a tensor-parallel
+// group reads only the columns / rows it streams.
+int upload_rows(M *m, FileReader &fr, uint64_t off, size_t rows, size_t row_stride, size_t col0, size_t cols, void *dst) {
     uint8_t *d = (uint8_t *)dst;
-    while (n) {
-        const size_t c = n < fr.pin_bytes ? n : fr.pin_bytes;
-        int rc = read_exact(fr.fd, fr.pin, c, off);
+    const size_t per = std::max<size_t>(1, fr.pin_bytes / cols);
+    for (size_t r = 0; r < rows; r += per) {
+        const size_t n = std::min(per, rows - r);
+        int rc = 0;
+        if (cols == row_stride) rc = read_exact(fr.fd, fr.pin, n * cols, off + r * row_stride);
+        else
+            for (size_t i = 0; i < n && !rc; ++i) rc = read_exact(fr.fd, fr.pin + i * cols, cols, off + (r + i) * row_stride + col0);
         if (rc) return rc;
-        CK(cudaMemcpyAsync(d, fr.pin, c, cudaMemcpyHostToDevice, m->stream));
+        CK(cudaMemcpyAsync(d + r * cols, fr.pin, n * cols, cudaMemcpyHostToDevice, m->stream));
         CK(cudaStreamSynchronize(m->stream));
-        d += c;
-        off += c;
-        n -= c;
     }
     return 0;
 }
@@ -314,21 +221,21 @@ template <class T> int upload_tensor(M *m, FileReader &fr, int tid, T **out) {
     const size_t n = binfmt::elems(tid, m->L, m->E);
     int rc = dmalloc(m, out, n);
     if (rc) return rc;
-    return upload(m, fr, binfmt::offset(tid, m->L, m->E), n * sizeof(T), *out);
+    return upload_rows(m, fr, binfmt::offset(tid, m->L, m->E), 1, n * sizeof(T), 0, n * sizeof(T), *out);
 }
 
-// uint8 matrix family `tid`: `mats` matrices of [rows_in][cols_out] -> int8 [cols_out][rows_in]
-int upload_matrix(M *m, FileReader &fr, int tid, size_t mats, size_t rows_in, size_t cols_out, uint8_t *d_raw,
-                  int8_t **out) {
-    int rc = dmalloc(m, out, mats * rows_in * cols_out);
+// uint8 matrix family `tid`: `mats` matrices stored [rows_in][cols_out]; this rank keeps input rows
+// [in0, in0 + nin) and output columns [out0, out0 + nout) -> int8 [nout][nin] per matrix.
+int upload_matrix(M *m, FileReader &fr, int tid, size_t mats, size_t rows_in, size_t cols_out, size_t in0, size_t nin,
+                  size_t out0, size_t nout, uint8_t *d_raw, int8_t **out) {
+    int rc = dmalloc(m, out, mats * nin * nout);
     if (rc) return rc;
     const uint64_t base = binfmt::offset(tid, m->L, m->E);
     for (size_t i = 0; i < mats; ++i) {
-        rc = upload(m, fr, base + i * rows_in * cols_out, rows_in * cols_out, d_raw);
+        rc = upload_rows(m, fr, base + i * rows_in * cols_out + in0 * cols_out, nin, cols_out, out0, nout, d_raw);
         if (rc) return rc;
-        dim3 g((unsigned)((cols_out + 63) / 64), (unsigned)((rows_in + 63) / 64));
-        rk::k_transpose_xor<<<g, 256, 0, m->stream>>>(d_raw, cols_out, (int)rows_in, (int)cols_out,
-                                                      *out + i * rows_in * cols_out, rows_in, 0);
+        dim3 g((unsigned)((nout + 63) / 64), (unsigned)((nin + 63) / 64));
+        rk::k_transpose_xor<<<g, 256, 0, m->stream>>>(d_raw, nout, (int)nin, (int)nout, *out + i * nin * nout, nin, 0);
         CK(cudaGetLastError());
         CK(cudaStreamSynchronize(m->stream));
     }
@@ -345,6 +252,15 @@ int centre(M *m, const float *r, const float *o, size_t n, const float **out) {
     return 0;
 }
 
+// Capacity checks of the per-CTA shared arrays for a grid of `grid` CTAs.
+bool grid_fits(unsigned long long E, unsigned long long Er, unsigned long long Vr, int grid) {
+    const unsigned long long g = (unsigned long long)grid;
+    const unsigned long long ne = (E + g - 1) / g + 1, nc = (Er + g - 1) / g + 1, nk = (4 * Er + g - 1) / g + 1, nv = (Vr + g - 1) / g + 1;
+    return grid >= 1 && grid <= rk::kMaxGrid && E >= g && ne <= (unsigned long long)rk::kMaxSlice &&
+           nk <= 160 && nk + nc <= (unsigned long long)rk::kMaxRowsPerCta && 4 * ne <= (unsigned long long)rk::kMaxRowsPerCta &&
+           3 * nc <= (unsigned long long)rk::kMaxRowsPerCta && nv <= (unsigned long long)rk::kMaxRowsPerCta;
+}
+
 int do_load(M *m, const char *path, int quiet) {
     FileReader fr;
     fr.fd = open(path, O_RDONLY);
@@ -354,13 +270,15 @@ int do_load(M *m, const char *path, int quiet) {
     if (rc) return rc;
     m->L = (unsigned long long)hdr[0];
     m->E = (unsigned long long)hdr[1];
-    const unsigned long long L = m->L, E = m->E;
+    const unsigned long long L = m->L, E = m->E, G = (unsigned long long)m->tp_size;
     if (!quiet) {
         printf("n_layers: %llu\nn_embed: %llu\n", L, E);
         fflush(stdout);
     }
     if (L == 0 || L > 4096 || E == 0 || E % 16 != 0 || E > 5120)
         return fail(5, "unsupported model shape: n_layers=%llu n_embed=%llu (need n_embed %% 16 == 0, <= 5120)", L, E);
+    if (E % (16 * G) != 0)
+        return fail(7, "tensor parallelism: n_embed=%llu is not a multiple of 16 x %llu ranks", E, G);
     struct stat st;
     if (fstat(fr.fd, &st) != 0 || (uint64_t)st.st_size < binfmt::file_bytes(L, E))
         return fail(4, "model file too short: %lld bytes, need %llu", (long long)st.st_size,
@@ -373,45 +291,47 @@ int do_load(M *m, const char *path, int quiet) {
     m->sms = prop.multiProcessorCount;
     m->grid = m->sms;
     CK(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
-
-    m->cpl = E <= 1024 ? 2 : E <= 2048 ? 4 : E <= 4096 ? 8 : 10;
-    if (const char *e = getenv("RWKV_B200_MODE")) {
-        if (std::string(e) == "staged" && m->tp_size == 1) m->token_mode = false;
+    {
+        int coop = 0;
+        CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, m->device));
+        if (!coop) return fail(6, "device does not support cooperative launch");
     }
+
+    const unsigned long long Er = E / G;
+    const unsigned long long V = binfmt::kVocab;
+    const unsigned long long v_lo = V * (unsigned long long)m->tp_rank / G, v_hi = V * ((unsigned long long)m->tp_rank + 1) / G;
+    const unsigned long long Vr = v_hi - v_lo;
+    m->cpl = chunks_per_lane(E);
     rk::Params &p = m->p;
     p.L = (int)L;
     p.E = (int)E;
+    p.G = (int)G;
+    p.rank = m->tp_rank;
+    p.Er = (int)Er;
+    p.Vr = (int)Vr;
+    p.vbase = (int)v_lo;
     p.plane_cap = (int)(12 * E);
-    configure_mode(m);
-    p.tp_rank = m->tp_rank;
-    p.tp_size = m->tp_size;
-    if ((4 * E + m->grid - 1) / m->grid + (E + m->grid - 1) / m->grid + 2 > (unsigned long long)rk::kMaxRowsPerCta ||
-        (E + m->grid - 1) / m->grid + 1 > (unsigned long long)rk::kMaxSlice ||
-        (4 * E + m->grid - 1) / m->grid + 1 > 2ull * rk::kConsumers ||
-        (binfmt::kVocab + m->grid - 1) / m->grid + 1 > (unsigned long long)rk::kMaxRowsPerCta ||
-        m->grid > rk::kRedMax || (4 * E + m->grid - 1) / m->grid + 1 > (unsigned long long)rk::kRedMax)
-        return fail(5, "grid of %d CTAs is too small for n_embed=%llu", m->grid, E);
-    switch (m->cpl) {
-    case 2: rc = set_attrs<2>(232448), rc = rc ? rc : set_attrs_tok<2>(232448); break;
-    case 4: rc = set_attrs<4>(232448), rc = rc ? rc : set_attrs_tok<4>(232448); break;
-    case 8: rc = set_attrs<8>(232448), rc = rc ? rc : set_attrs_tok<8>(232448); break;
-    default: rc = set_attrs<10>(232448), rc = rc ? rc : set_attrs_tok<10>(232448); break;
+    p.timeout_ms = G > 1 ? 60000u : 4000u;
+    configure_ring(m);
+    if (p.stages < 2) return fail(5, "n_embed=%llu leaves no room for a two-stage ring", E);
+    if (!grid_fits(E, Er, Vr, m->grid)) return fail(5, "a grid of %d CTAs does not fit n_embed=%llu", m->grid, E);
+    const bool full = E == (unsigned long long)m->cpl * 512ull;
+    for (int tr = 0; tr < 2; ++tr) {
+        const void *fn = token_entry(m->cpl, full, tr != 0);
+        if (!fn) return fail(3, "no kernel for %d chunks per lane", m->cpl);
+        CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, rk::kSmemLimit));
     }
-    if (rc) return rc;
 
     fr.pin_bytes = 64u << 20;
     CK(cudaMallocHost((void **)&fr.pin, fr.pin_bytes));
 
-    auto say = [&](int tid) {
-        if (!quiet) {
-            printf("loading: %s\n", binfmt::name(tid));
-            fflush(stdout);
-        }
-    };
     // The reference prints every tensor in file order (rwkv.cu:679); keep that UX.
-    for (int t = 0; t < binfmt::kNumTensors; ++t) say(t);
+    if (!quiet) {
+        for (int t = 0; t < binfmt::kNumTensors; ++t) printf("loading: %s\n", binfmt::name(t));
+        fflush(stdout);
+    }
 
-    // ---- small parameter tensors, reference dtype and shape ---------------------------------
+    // ---- small parameter tensors, reference dtype and shape (replicated on every rank) ----------
     float *emb, *kr, *vr, *rr, *o1, *o2, *o3, *aor, *aoo, *fkr, *fvr, *frr, *fko, *fvo, *fro, *hr, *ho;
     double *ln, *mixk, *mixv, *mixr, *fmk, *fmr, *decay, *bonus;
 #define UP(tid, var)                                                                               \
@@ -442,19 +362,20 @@ int do_load(M *m, const char *path, int quiet) {
     if ((rc = centre(m, frr, fro, L * E, &p.ocfr))) return rc;
     if ((rc = centre(m, hr, ho, E, &p.ochead))) return rc;
 
-    // ---- uint8 matrices: stage raw, transpose + centre on the device --------------------------
+    // ---- uint8 matrices: this rank's slices; stage raw, transpose + centre on the device ----------
     uint8_t *d_raw = nullptr;
-    const size_t raw_bytes = std::max<size_t>(4 * E * E, binfmt::kVocab * E);
+    const size_t raw_bytes = std::max<size_t>(4 * Er * E, Vr * E);
     CK(cudaMalloc((void **)&d_raw, raw_bytes));
+    const size_t c0 = (size_t)m->tp_rank * Er; // first channel of this rank
     int8_t *wk, *wv, *wr, *wo, *wfk, *wfv, *wfr, *whead;
-    rc = upload_matrix(m, fr, KM, L, E, E, d_raw, &wk);
-    if (!rc) rc = upload_matrix(m, fr, VM, L, E, E, d_raw, &wv);
-    if (!rc) rc = upload_matrix(m, fr, RM, L, E, E, d_raw, &wr);
-    if (!rc) rc = upload_matrix(m, fr, ATTOUT, L, E, E, d_raw, &wo);
-    if (!rc) rc = upload_matrix(m, fr, FFNK, L, E, 4 * E, d_raw, &wfk);
-    if (!rc) rc = upload_matrix(m, fr, FFNV, L, 4 * E, E, d_raw, &wfv);
-    if (!rc) rc = upload_matrix(m, fr, FFNR, L, E, E, d_raw, &wfr);
-    if (!rc) rc = upload_matrix(m, fr, HEAD, 1, E, binfmt::kVocab, d_raw, &whead);
+    rc = upload_matrix(m, fr, KM, L, E, E, 0, E, c0, Er, d_raw, &wk);                         // column split
+    if (!rc) rc = upload_matrix(m, fr, VM, L, E, E, 0, E, c0, Er, d_raw, &wv);
+    if (!rc) rc = upload_matrix(m, fr, RM, L, E, E, 0, E, c0, Er, d_raw, &wr);
+    if (!rc) rc = upload_matrix(m, fr, ATTOUT, L, E, E, c0, Er, 0, E, d_raw, &wo);             // row split
+    if (!rc) rc = upload_matrix(m, fr, FFNK, L, E, 4 * E, 0, E, 4 * c0, 4 * Er, d_raw, &wfk);  // column split
+    if (!rc) rc = upload_matrix(m, fr, FFNV, L, 4 * E, E, 4 * c0, 4 * Er, 0, E, d_raw, &wfv);  // row split
+    if (!rc) rc = upload_matrix(m, fr, FFNR, L, E, E, 0, E, c0, Er, d_raw, &wfr);              // column split
+    if (!rc) rc = upload_matrix(m, fr, HEAD, 1, E, V, 0, E, v_lo, Vr, d_raw, &whead);          // column split
     cudaFree(d_raw);
     if (rc) return rc;
     p.wk = wk; p.wv = wv; p.wr = wr; p.wo = wo; p.wfk = wfk; p.wfv = wfv; p.wfr = wfr; p.whead = whead;
@@ -463,49 +384,56 @@ int do_load(M *m, const char *path, int quiet) {
 
     // ---- state, activations, control ------------------------------------------------------------
     const size_t sn = (size_t)(L * E * m->max_gpt);
-    if ((rc = dmalloc(m, &p.sxy, sn)) || (rc = dmalloc(m, &p.saa, sn)) || (rc = dmalloc(m, &p.sbb, sn)) ||
-        (rc = dmalloc(m, &p.sdd, sn)) || (rc = dmalloc(m, &m->spp, sn)))
-        return rc;
-    for (double *s : {p.sxy, p.saa, p.sbb, p.sdd, m->spp}) CK(cudaMemsetAsync(s, 0, sn * sizeof(double), m->stream));
+    if ((rc = dmalloc(m, &p.sxy, sn)) || (rc = dmalloc(m, &p.sdd, sn)) || (rc = dmalloc(m, &m->spp, sn))) return rc;
+    for (double *s : {p.sxy, p.sdd, m->spp}) CK(cudaMemsetAsync(s, 0, sn * sizeof(double), m->stream));
     double *b1, *fkb, *fvb;
-    float *b3;
-    if ((rc = dmalloc(m, &p.x, E)) || (rc = dmalloc(m, &p.xy_new, E)) || (rc = dmalloc(m, &p.dd_new, E)) ||
-        (rc = dmalloc(m, &p.xs_o, E)) || (rc = dmalloc(m, &p.sr, E)) || (rc = dmalloc(m, &p.xs_v, 4 * E)) ||
-        (rc = dmalloc(m, &p.part_o, 2 * rk::kMaxGrid)) ||
-        (rc = dmalloc(m, &p.part_v, 2 * rk::kMaxGrid)) || (rc = dmalloc(m, &p.ctrl, 1)) ||
-        (rc = dmalloc(m, &b1, E)) || (rc = dmalloc(m, &fkb, E)) || (rc = dmalloc(m, &fvb, E)) ||
-        (rc = dmalloc(m, &b3, E)))
+    float *b3, *b4, *frb;
+    if ((rc = dmalloc(m, &p.x, E)) || (rc = dmalloc(m, &p.ctrl, 1)) || (rc = dmalloc(m, &b1, E)) || (rc = dmalloc(m, &fkb, E)) ||
+        (rc = dmalloc(m, &fvb, E)) || (rc = dmalloc(m, &b3, E)) || (rc = dmalloc(m, &b4, E)) || (rc = dmalloc(m, &frb, 4 * E)))
         return rc;
     CK(cudaMemsetAsync(p.ctrl, 0, sizeof(rk::Ctrl), m->stream));
-    // exchange block: [0,64) barrier counter, [64,128) rank-local arrival counter | [128,512) accumulators | [1024, +32E) vec | logits
+    CK(cudaMemsetAsync(p.x, 0, E * sizeof(double), m->stream));
+    // exchange block: one allocation, same layout on every rank (exchange.cuh)
     {
+        size_t off = 256;
+        auto take = [&](size_t bytes) {
+            const size_t o = off;
+            off = (off + bytes + 255) & ~(size_t)255;
+            return o;
+        };
+        const size_t nb = (size_t)m->grid;
+        for (int i = 0; i < 2; ++i) p.off_stat[i] = (unsigned int)take(nb * sizeof(rk::StatRec));
+        for (int i = 0; i < 5; ++i) p.off_off[i] = (unsigned int)take(nb * sizeof(rk::OffRec));
+        const size_t vlen[5] = {3 * E, Er, 2 * E, 4 * Er, E};
+        for (int i = 0; i < 5; ++i) p.off_vec[i] = (unsigned int)take(vlen[i] * 4);
+        for (int i = 0; i < 2; ++i) p.off_in[i] = (unsigned int)take(G * E * sizeof(rk::TaggedDouble));
+        p.off_sr = (unsigned int)take(E * 8);
+        p.off_arg = (unsigned int)take(G * nb * sizeof(rk::TaggedDouble));
+        p.off_done = (unsigned int)take(G * nb * 8);
+        p.off_logits = (unsigned int)take(V * 4);
+        p.off_saa = take(sn * 8);
+        p.off_sbb = take(sn * 8);
+        m->xch_bytes = off;
         unsigned char *x = nullptr;
-        m->xch_bytes = (1024 + 32 * (size_t)E + 4 * (size_t)binfmt::kVocab + 255) & ~(size_t)255;
         if ((rc = dmalloc(m, &x, m->xch_bytes))) return rc;
         CK(cudaMemsetAsync(x, 0, m->xch_bytes, m->stream));
-        for (int g = 0; g < 8; ++g) p.xch[g] = x; // peers are wired by rwkv_b200_tp_import
-        p.gbar = reinterpret_cast<unsigned int *>(x);
-        p.lbar = reinterpret_cast<unsigned int *>(x + 64);
-        p.acc = reinterpret_cast<unsigned long long *>(x + 128);
-        p.vec = reinterpret_cast<float *>(x + 1024);
-        p.logits = reinterpret_cast<float *>(x + 1024 + 32 * (size_t)E);
+        for (int g = 0; g < rk::kMaxRanks; ++g) p.xch[g] = x; // peers are wired by rwkv_b200_tp_import
     }
-    {
-        int coop = 0;
-        CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, m->device));
-        if (!coop && m->token_mode) return fail(6, "device does not support cooperative launch");
-    }
-    CK(cudaMemsetAsync(p.x, 0, E * sizeof(double), m->stream));
+    float *logits = reinterpret_cast<float *>(p.xch[0] + p.off_logits);
+    double *saa = reinterpret_cast<double *>(p.xch[0] + p.off_saa), *sbb = reinterpret_cast<double *>(p.xch[0] + p.off_sbb);
     m->tensors[X] = p.x;
-    m->tensors[STATEXY] = p.sxy; m->tensors[STATEAA] = p.saa; m->tensors[STATEBB] = p.sbb;
+    m->tensors[STATEXY] = p.sxy; m->tensors[STATEAA] = saa; m->tensors[STATEBB] = sbb;
     m->tensors[STATEPP] = m->spp; m->tensors[STATEDD] = p.sdd;
-    m->tensors[BUFFER1] = b1; m->tensors[BUFFER2] = p.logits; m->tensors[BUFFER3] = b3; m->tensors[BUFFER4] = p.sr;
-    m->tensors[FFNKBUFFER] = fkb; m->tensors[FFNVBUFFER] = fvb; m->tensors[FFNRBUFFER] = p.xs_v;
+    m->tensors[BUFFER1] = b1; m->tensors[BUFFER2] = logits; m->tensors[BUFFER3] = b3; m->tensors[BUFFER4] = b4;
+    m->tensors[FFNKBUFFER] = fkb; m->tensors[FFNVBUFFER] = fvb; m->tensors[FFNRBUFFER] = frb;
 
     CK(cudaMallocHost((void **)&m->h_ctrl, sizeof(rk::Ctrl) * m->max_gpt));
-    CK(cudaMallocHost((void **)&m->h_logits, sizeof(float) * binfmt::kVocab * m->max_gpt));
+    CK(cudaMallocHost((void **)&m->h_logits, sizeof(float) * V * m->max_gpt));
     CK(cudaMallocHost((void **)&m->h_next, sizeof(unsigned long long)));
-    memset(m->h_logits, 0, sizeof(float) * binfmt::kVocab * m->max_gpt);
+    CK(cudaHostAlloc((void **)&m->h_diag, sizeof(rk::Diag), cudaHostAllocMapped));
+    memset(m->h_diag, 0, sizeof(rk::Diag));
+    CK(cudaHostGetDevicePointer((void **)&p.diag, m->h_diag, 0));
+    memset(m->h_logits, 0, sizeof(float) * V * m->max_gpt);
     CK(cudaStreamSynchronize(m->stream));
     return 0;
 }
@@ -515,6 +443,8 @@ int check_model(const M *m) {
     return 0;
 }
 
+float *dev_logits(M *m) { return reinterpret_cast<float *>(m->p.xch[m->tp_rank] + m->p.off_logits); }
+
 } // namespace
 
 // =================================================================================================
@@ -523,7 +453,7 @@ int check_model(const M *m) {
 extern "C" {
 
 const char *rwkv_b200_last_error(void) { return g_err.c_str(); }
-int rwkv_b200_abi_version(void) { return 1; }
+int rwkv_b200_abi_version(void) { return 2; }
 
 int rwkv_b200_device_count(void) {
     int n = 0;
@@ -538,7 +468,7 @@ int rwkv_b200_load_tp(const char *path, unsigned long long max_gpt, int device, 
                       rwkv_b200_model **out, unsigned long long *n_layers, unsigned long long *n_embed) {
     if (!path || !out) return fail(1, "null argument");
     *out = nullptr;
-    if (tp_size < 1 || tp_size > 8 || tp_rank < 0 || tp_rank >= tp_size)
+    if (tp_size < 1 || tp_size > rk::kMaxRanks || tp_rank < 0 || tp_rank >= tp_size)
         return fail(7, "tensor parallelism: rank %d of %d is not supported (1..8 ranks)", tp_rank, tp_size);
     if (rwkv_b200_device_count() <= device || device < 0)
         return fail(6, "CUDA device %d not available (no CPU fallback exists)", device);
@@ -569,14 +499,16 @@ void rwkv_b200_free(rwkv_b200_model *m) {
     if (!m) return;
     cudaSetDevice(m->device);
     if (m->stream) cudaStreamSynchronize(m->stream);
-    drop_graphs(m);
+    rk::prefill_free(m->pf);
     for (void *p : m->ipc_opened) cudaIpcCloseMemHandle(p);
     for (void *p : m->allocs) cudaFree(p);
     if (m->h_ctrl) cudaFreeHost(m->h_ctrl);
     if (m->h_logits) cudaFreeHost(m->h_logits);
     if (m->h_next) cudaFreeHost(m->h_next);
     if (m->h_sample) cudaFreeHost(m->h_sample);
+    if (m->h_diag) cudaFreeHost(m->h_diag);
     if (m->stream) cudaStreamDestroy(m->stream);
+    cudaGetLastError(); // a context killed by a trap makes every call above fail; do not leave that as "last error"
     delete m;
 }
 
@@ -619,10 +551,10 @@ int rwkv_b200_state_upload(rwkv_b200_model *m, const double *xy, const double *a
     CK(cudaSetDevice(m->device));
     const size_t n = (size_t)(m->L * m->E * slots) * sizeof(double);
     const double *src[5] = {xy, aa, bb, pp, dd};
-    double *dst[5] = {m->p.sxy, m->p.saa, m->p.sbb, m->spp, m->p.sdd};
+    double *dst[5] = {m->p.sxy, (double *)m->tensors[STATEAA], (double *)m->tensors[STATEBB], m->spp, m->p.sdd};
     for (int i = 0; i < 5; ++i)
         if (src[i]) CK(cudaMemcpyAsync(dst[i], src[i], n, cudaMemcpyHostToDevice, m->stream));
-    CK(cudaStreamSynchronize(m->stream));
+    SYNC(m);
     return 0;
 }
 
@@ -634,10 +566,10 @@ int rwkv_b200_state_download(rwkv_b200_model *m, double *xy, double *aa, double 
     CK(cudaSetDevice(m->device));
     const size_t n = (size_t)(m->L * m->E * slots) * sizeof(double);
     double *dst[5] = {xy, aa, bb, pp, dd};
-    const double *src[5] = {m->p.sxy, m->p.saa, m->p.sbb, m->spp, m->p.sdd};
+    const double *src[5] = {m->p.sxy, (double *)m->tensors[STATEAA], (double *)m->tensors[STATEBB], m->spp, m->p.sdd};
     for (int i = 0; i < 5; ++i)
         if (dst[i]) CK(cudaMemcpyAsync(dst[i], src[i], n, cudaMemcpyDeviceToHost, m->stream));
-    CK(cudaStreamSynchronize(m->stream));
+    SYNC(m);
     return 0;
 }
 
@@ -646,8 +578,9 @@ int rwkv_b200_state_zero(rwkv_b200_model *m) {
     if (rc) return rc;
     CK(cudaSetDevice(m->device));
     const size_t n = (size_t)(m->L * m->E * m->max_gpt) * sizeof(double);
-    for (double *s : {m->p.sxy, m->p.saa, m->p.sbb, m->p.sdd, m->spp}) CK(cudaMemsetAsync(s, 0, n, m->stream));
-    CK(cudaStreamSynchronize(m->stream));
+    for (double *s : {m->p.sxy, (double *)m->tensors[STATEAA], (double *)m->tensors[STATEBB], m->p.sdd, m->spp})
+        CK(cudaMemsetAsync(s, 0, n, m->stream));
+    SYNC(m);
     return 0;
 }
 
@@ -659,19 +592,29 @@ int rwkv_b200_forward(rwkv_b200_model *m, const unsigned long long *tokens, unsi
     if (n_tokens > m->max_gpt) return fail(1, "Context too large, max context is %llu", m->max_gpt);
     CK(cudaSetDevice(m->device));
     const size_t V = binfmt::kVocab;
-    for (unsigned long long t = 0; t < n_tokens; ++t) {
+    for (unsigned long long t = 0; t < n_tokens; ++t)
         if (tokens[t] >= V) return fail(1, "token id %llu out of range", tokens[t]);
+    if (n_tokens >= (unsigned long long)rk::kPrefillMinTokens && m->tp_size == 1 && rk::prefill_enabled(m->pf)) {
+        rc = rk::prefill_forward(m->pf, m->p, m->stream, tokens, (int)n_tokens, mode == RWKV_B200_MODE_PARRALEL,
+                                 logits_out ? m->h_logits : nullptr);
+        if (rc) return fail(rc, "%s", rk::prefill_error());
+        m->launches += rk::prefill_launches(m->pf);
+        SYNC(m);
+        if (logits_out && logits_out != m->h_logits) memcpy(logits_out, m->h_logits, n_tokens * V * sizeof(float));
+        return 0;
+    }
+    for (unsigned long long t = 0; t < n_tokens; ++t) {
         rk::Ctrl &c = m->h_ctrl[t];
         c.token = tokens[t];
         c.next = 0;
         c.slot = (mode == RWKV_B200_MODE_PARRALEL) ? t : 0;
         c.pos = 0;
-        CK(cudaMemcpyAsync(m->p.ctrl, &c, 32, cudaMemcpyHostToDevice, m->stream));
-        if ((rc = run_token(m, false))) return rc;
+        CK(cudaMemcpyAsync(m->p.ctrl, &c, sizeof(rk::Ctrl), cudaMemcpyHostToDevice, m->stream));
+        if ((rc = launch_token(m, 0, false, nullptr, m->stream))) return rc;
         if (logits_out)
-            CK(cudaMemcpyAsync(m->h_logits + t * V, m->p.logits, V * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
+            CK(cudaMemcpyAsync(m->h_logits + t * V, dev_logits(m), V * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
     }
-    CK(cudaStreamSynchronize(m->stream));
+    SYNC(m);
     if (logits_out && logits_out != m->h_logits) memcpy(logits_out, m->h_logits, n_tokens * V * sizeof(float));
     return 0;
 }
@@ -687,11 +630,11 @@ int rwkv_b200_forward_greedy(rwkv_b200_model *m, unsigned long long token, unsig
     c.next = 0;
     c.slot = 0;
     c.pos = 0;
-    CK(cudaMemcpyAsync(m->p.ctrl, &c, 32, cudaMemcpyHostToDevice, m->stream));
-    if ((rc = run_token(m, true))) return rc;
+    CK(cudaMemcpyAsync(m->p.ctrl, &c, sizeof(rk::Ctrl), cudaMemcpyHostToDevice, m->stream));
+    if ((rc = launch_token(m, 0, true, nullptr, m->stream))) return rc;
     CK(cudaMemcpyAsync(m->h_next, &m->p.ctrl->next, sizeof(unsigned long long), cudaMemcpyDeviceToHost, m->stream));
-    if (logits_out) CK(cudaMemcpyAsync(m->h_logits, m->p.logits, V * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
-    CK(cudaStreamSynchronize(m->stream));
+    if (logits_out) CK(cudaMemcpyAsync(m->h_logits, dev_logits(m), V * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
+    SYNC(m);
     if (next) *next = *m->h_next;
     if (logits_out && logits_out != m->h_logits) memcpy(logits_out, m->h_logits, V * sizeof(float));
     return 0;
@@ -710,10 +653,10 @@ int rwkv_b200_sample_typical(rwkv_b200_model *m, float temp, double u, unsigned 
     }
     // the reference applies the temperature as probs ^ uint8(1 / temp) (include/rwkv/sampler/typical.h)
     const int exponent = temp != 1.0f ? (int)(unsigned char)(1.0 / (double)temp) : 1;
-    rk::k_sample_typical<<<1, rk::kSampleThreads, 0, m->stream>>>(m->p.logits, (int)binfmt::kVocab, exponent, u, m->d_sample);
+    rk::k_sample_typical<<<1, rk::kSampleThreads, 0, m->stream>>>(dev_logits(m), (int)binfmt::kVocab, exponent, u, m->d_sample);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(m->h_sample, m->d_sample, 2 * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
-    CK(cudaStreamSynchronize(m->stream));
+    SYNC(m);
     *token = (unsigned long long)m->h_sample[0];
     if (margin) *margin = m->h_sample[1];
     m->launches += 1;
@@ -726,50 +669,35 @@ int rwkv_b200_decode_timed(rwkv_b200_model *m, const unsigned long long *tokens,
     if (rc) return rc;
     if (!tokens || n == 0 || !ms) return fail(1, "decode_timed: bad arguments");
     CK(cudaSetDevice(m->device));
-    unsigned long long *d_tok = nullptr;
     const unsigned long long cnt = teacher_forced ? n : 1;
     for (unsigned long long i = 0; i < cnt; ++i)
         if (tokens[i] >= binfmt::kVocab) return fail(1, "token id %llu out of range", tokens[i]);
-    CK(cudaMalloc((void **)&d_tok, cnt * sizeof(unsigned long long)));
-    CK(cudaMemcpy(d_tok, tokens, cnt * sizeof(unsigned long long), cudaMemcpyHostToDevice));
-    rk::Ctrl c{tokens[0], tokens[0], 0, 0, 0, {0, 0, 0}};
-    CK(cudaStreamSynchronize(m->stream));
-    CK(cudaMemcpy(m->p.ctrl, &c, 32, cudaMemcpyHostToDevice));
-    cudaGraphExec_t g = nullptr;
-    if (!m->token_mode) {
-        rc = build_graph(m, teacher_forced ? G_STREAM : G_FREE, d_tok, &g);
-        if (rc) {
-            cudaFree(d_tok);
-            return rc;
-        }
-    }
-    cudaEvent_t a, b;
-    cudaEventCreate(&a);
-    cudaEventCreate(&b);
-    cudaStreamSynchronize(m->stream);
-    cudaEventRecord(a, m->stream);
-    cudaError_t e = cudaSuccess;
-    for (unsigned long long i = 0; i < n && e == cudaSuccess; ++i) {
-        if (m->token_mode) {
-            if (launch_token(m, teacher_forced ? 2 : 1, !teacher_forced, d_tok, m->stream)) e = cudaErrorLaunchFailure;
-        } else {
-            e = cudaGraphLaunch(g, m->stream);
-        }
-    }
-    cudaEventRecord(b, m->stream);
+    unsigned long long *d_tok = nullptr;
+    cudaEvent_t a = nullptr, b = nullptr;
+    cudaError_t e = cudaMalloc((void **)&d_tok, cnt * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemcpy(d_tok, tokens, cnt * sizeof(unsigned long long), cudaMemcpyHostToDevice);
+    rk::Ctrl c{tokens[0], tokens[0], 0, 0};
     if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);
-    if (e == cudaSuccess) cudaEventElapsedTime(ms, a, b);
-    cudaEventDestroy(a);
-    cudaEventDestroy(b);
-    if (g) cudaGraphExecDestroy(g);
-    cudaFree(d_tok);
-    if (e != cudaSuccess) return fail(100 + (int)e, "decode_timed failed: %s", cudaGetErrorString(e));
-    m->launches += n * (kernels_per_token(m, !teacher_forced) + (m->token_mode ? 0 : 1));
+    if (e == cudaSuccess) e = cudaMemcpy(m->p.ctrl, &c, sizeof(rk::Ctrl), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaEventCreate(&a);
+    if (e == cudaSuccess) e = cudaEventCreate(&b);
+    if (e == cudaSuccess) e = cudaEventRecord(a, m->stream);
+    rc = 0;
+    for (unsigned long long i = 0; i < n && e == cudaSuccess && rc == 0; ++i)
+        rc = launch_token(m, teacher_forced ? 2 : 1, !teacher_forced, d_tok, m->stream);
+    if (e == cudaSuccess && rc == 0) e = cudaEventRecord(b, m->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);
+    if (e == cudaSuccess && rc == 0) e = cudaEventElapsedTime(ms, a, b);
+    if (a) cudaEventDestroy(a);
+    if (b) cudaEventDestroy(b);
+    if (d_tok) cudaFree(d_tok);
+    if (rc) return rc;
+    if (e != cudaSuccess) return sync_failed(m, e, "decode_timed");
     return 0;
 }
 
-int rwkv_b200_kernel_count(void) { return K_COUNT; }
-const char *rwkv_b200_kernel_name(int k) { return (k >= 0 && k < K_COUNT) ? kKernelNames[k] : ""; }
+int rwkv_b200_kernel_count(void) { return 1; }
+const char *rwkv_b200_kernel_name(int k) { return k == 0 ? kKernelNames[0] : ""; }
 
 int rwkv_b200_profile(rwkv_b200_model *m, const unsigned long long *tokens, unsigned long long n, float *ms_sum,
                       unsigned long long *launches, double *bytes) {
@@ -777,58 +705,36 @@ int rwkv_b200_profile(rwkv_b200_model *m, const unsigned long long *tokens, unsi
     if (rc) return rc;
     if (!tokens || !ms_sum || !launches || !bytes) return fail(1, "profile: bad arguments");
     CK(cudaSetDevice(m->device));
-    for (int k = 0; k < K_COUNT; ++k) {
-        ms_sum[k] = 0.f;
-        launches[k] = 0;
-    }
-    const double E = (double)m->E, V = (double)binfmt::kVocab;
-    // algorithmic HBM bytes of one launch: weight bytes + the vectors the phase must touch
-    bytes[K_EMBED] = 4 * E + 16 * E + 8 * E;
-    bytes[K_ATT_KVR] = 3 * E * E + E * (8 + 16 + 8 + 24 + 12 + 12) + E * (8 * 4 + 8 + 4);
-    bytes[K_ATT_OUT] = E * E + E * (4 + 4 + 16 + 16);
-    bytes[K_FFN_RK] = 5 * E * E + E * (8 + 16 + 8 + 16 + 8 + 8) + E * 8 + E * 4 + 4 * E * (4 + 4 + 4);
-    bytes[K_FFN_V] = 4 * E * E + 4 * E * 4 + E * (4 + 16 + 16);
-    bytes[K_HEAD] = V * E + E * (8 + 16 + 8) + 4 * V;
-    bytes[K_ARGMAX] = 4 * V;
-    bytes[K_TOKEN] = (double)binfmt::algorithmic_bytes_per_token(m->L, m->E);
-    for (unsigned long long t = 0; t < n; ++t) {
-        if (tokens[t] >= binfmt::kVocab) return fail(1, "token id out of range");
-        rk::Ctrl c{tokens[t], 0, 0, 0, 0, {0, 0, 0}};
-        if (m->token_mode) {
-            CK(cudaMemcpyAsync(m->p.ctrl, &c, 32, cudaMemcpyHostToDevice, m->stream));
-            cudaEvent_t a, b;
-            CK(cudaEventCreate(&a));
-            CK(cudaEventCreate(&b));
-            CK(cudaStreamSynchronize(m->stream));
-            CK(cudaEventRecord(a, m->stream));
-            if ((rc = launch_token(m, 0, true, nullptr, m->stream))) return rc;
-            CK(cudaEventRecord(b, m->stream));
-            CK(cudaStreamSynchronize(m->stream));
-            float t_ms = 0.f;
-            cudaEventElapsedTime(&t_ms, a, b);
-            cudaEventDestroy(a);
-            cudaEventDestroy(b);
-            ms_sum[K_TOKEN] += t_ms;
-            launches[K_TOKEN] += 1;
-            m->launches += 1;
-            continue;
+    ms_sum[0] = 0.f;
+    launches[0] = 0;
+    // algorithmic HBM bytes of one launch on this rank: its share of the weights + the vectors
+    const double E = (double)m->E, V = (double)binfmt::kVocab, L = (double)m->L, G = (double)m->tp_size;
+    bytes[0] = (13.0 * L * E * E + V * E) / G + ((double)binfmt::algorithmic_bytes_per_token(m->L, m->E) - (13.0 * L * E * E + V * E));
+    cudaEvent_t a = nullptr, b = nullptr;
+    CK(cudaEventCreate(&a));
+    cudaError_t e = cudaEventCreate(&b);
+    rc = 0;
+    for (unsigned long long t = 0; t < n && e == cudaSuccess && rc == 0; ++t) {
+        if (tokens[t] >= binfmt::kVocab) {
+            rc = fail(1, "token id out of range");
+            break;
         }
-        CK(cudaMemcpyAsync(m->p.ctrl, &c, 32, cudaMemcpyHostToDevice, m->stream));
-        CK(cudaStreamSynchronize(m->stream));
-        Prof prof;
-        rc = enqueue_token(m, m->stream, true, &prof);
-        if (rc) return rc;
-        CK(cudaStreamSynchronize(m->stream));
-        for (auto &pe : prof.ev) {
-            float t_ms = 0.f;
-            cudaEventElapsedTime(&t_ms, pe.second.a, pe.second.b);
-            ms_sum[pe.first] += t_ms;
-            launches[pe.first] += 1;
-            cudaEventDestroy(pe.second.a);
-            cudaEventDestroy(pe.second.b);
-        }
-        m->launches += kernels_per_token(m, true);
+        rk::Ctrl c{tokens[t], 0, 0, 0};
+        e = cudaMemcpyAsync(m->p.ctrl, &c, sizeof(rk::Ctrl), cudaMemcpyHostToDevice, m->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);
+        if (e == cudaSuccess) e = cudaEventRecord(a, m->stream);
+        if (e == cudaSuccess) rc = launch_token(m, 0, true, nullptr, m->stream);
+        if (e == cudaSuccess && rc == 0) e = cudaEventRecord(b, m->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);
+        float t_ms = 0.f;
+        if (e == cudaSuccess && rc == 0) e = cudaEventElapsedTime(&t_ms, a, b);
+        ms_sum[0] += t_ms;
+        launches[0] += 1;
     }
+    cudaEventDestroy(a);
+    if (b) cudaEventDestroy(b);
+    if (rc) return rc;
+    if (e != cudaSuccess) return sync_failed(m, e, "profile");
     return 0;
 }
 
@@ -840,54 +746,36 @@ int rwkv_b200_set_option(rwkv_b200_model *m, const char *key, const char *value)
     if (!key || !value) return fail(1, "set_option: null");
     const std::string k = key;
     const int v = atoi(value);
-    if (k == "graph") m->use_graph = v != 0;
-    else if (k == "trace") {
+    if (k == "trace") {
         if (v && !m->p.trace) {
             unsigned long long *t = nullptr;
             if (dmalloc(m, &t, (size_t)rk::kMaxGrid * rk::kTraceMax)) return fail(1, "trace alloc failed");
             cudaMemset(t, 0, (size_t)rk::kMaxGrid * rk::kTraceMax * 8);
             m->p.trace = t;
             unsigned long long *pt = nullptr;
-            if (dmalloc(m, &pt, (size_t)3 * rk::kRedMax * rk::kTileTraceMax)) return fail(1, "trace alloc failed");
-            cudaMemset(pt, 0, (size_t)3 * rk::kRedMax * rk::kTileTraceMax * 8);
+            if (dmalloc(m, &pt, (size_t)2 * rk::kMaxGrid * rk::kTileTraceMax)) return fail(1, "trace alloc failed");
+            cudaMemset(pt, 0, (size_t)2 * rk::kMaxGrid * rk::kTileTraceMax * 8);
             m->p.ptrace = pt;
         } else if (!v) {
             m->p.trace = nullptr;
             m->p.ptrace = nullptr;
         }
-    } else if (k == "mode") {
-        const bool want_token = std::string(value) == "token";
-        if (!want_token && std::string(value) != "staged") return fail(1, "mode must be 'token' or 'staged'");
-        if (!want_token && m->tp_size > 1) return fail(1, "the staged kernels are single-GPU only");
-        m->token_mode = want_token;
-        configure_mode(m);
-    }
-    else if (k == "max_layers") m->max_layers = v;
+    } else if (k == "max_layers") m->max_layers = v;
     else if (k == "issue_gap") {
         if (v < 0 || v > 100000) return fail(1, "issue_gap is a cycle count in 0..100000");
         m->p.issue_gap = v;
-    }
-    else if (k == "stages") {
+    } else if (k == "timeout_ms") {
+        if (v < 1) return fail(1, "timeout_ms must be positive");
+        m->p.timeout_ms = (unsigned int)v;
+    } else if (k == "stages") {
         if (v < 2 || v > rk::kMaxStages) return fail(1, "stages must be 2..%d", rk::kMaxStages);
         const size_t smem = rk::smem_bytes(v, m->p.tile_bytes, m->p.plane_cap);
-        if (smem > 232448) return fail(1, "stages=%d needs %zu bytes of shared memory", v, smem);
+        if (smem > (size_t)rk::kSmemLimit) return fail(1, "stages=%d needs %zu bytes of shared memory", v, smem);
         m->p.stages = v;
         m->smem = smem;
-    } else if (k == "tile_bytes") {
-        if (m->token_mode) return fail(1, "the token kernel's tile is fixed at 8*n_embed bytes");
-        if (v < (int)(4 * m->E) || v % 16) return fail(1, "tile_bytes must be a multiple of 16 and >= 4*n_embed");
-        int st = m->p.stages;
-        while (st > 2 && rk::smem_bytes(st, v, m->p.plane_cap) > 232448) --st;
-        const size_t smem = rk::smem_bytes(st, v, m->p.plane_cap);
-        if (smem > 232448) return fail(1, "tile_bytes=%d needs %zu bytes of shared memory", v, smem);
-        m->p.tile_bytes = v;
-        m->p.stages = st;
-        m->smem = smem;
-    } else if (k == "grid") {
-        if (v < 1 || v > rk::kMaxGrid) return fail(1, "grid out of range");
-        m->grid = v;
+    } else if (k == "prefill") {
+        m->pf.disabled = v == 0;
     } else return fail(1, "unknown option '%s'", key);
-    drop_graphs(m);
     return 0;
 }
 
@@ -900,14 +788,9 @@ long long rwkv_b200_debug_read(rwkv_b200_model *m, const char *name, void *dst, 
     size_t bytes = 0, count = 0;
     const size_t E = m->E;
     if (k == "x") src = m->p.x, count = E, bytes = E * 8;
-    else if (k == "xy_new") src = m->p.xy_new, count = E, bytes = E * 8;
-    else if (k == "dd_new") src = m->p.dd_new, count = E, bytes = E * 8;
-    else if (k == "xs_o") src = m->p.xs_o, count = E, bytes = E * 4;
-    else if (k == "sr") src = m->p.sr, count = E, bytes = E * 4;
-    else if (k == "xs_v") src = m->p.xs_v, count = 4 * E, bytes = 16 * E;
-    else if (k == "logits") src = m->p.logits, count = binfmt::kVocab, bytes = 4 * binfmt::kVocab;
+    else if (k == "logits") src = dev_logits(m), count = binfmt::kVocab, bytes = 4 * binfmt::kVocab;
     else if (k == "trace" && m->p.trace) src = m->p.trace, count = (size_t)m->grid * rk::kTraceMax, bytes = count * 8;
-    else if (k == "ptrace" && m->p.ptrace) src = m->p.ptrace, count = (size_t)3 * m->grid * rk::kTileTraceMax, bytes = count * 8;
+    else if (k == "ptrace" && m->p.ptrace) src = m->p.ptrace, count = (size_t)2 * m->grid * rk::kTileTraceMax, bytes = count * 8;
     else return -1;
     if (dst_bytes < bytes) return -1;
     if (cudaStreamSynchronize(m->stream) != cudaSuccess) return -1;
@@ -943,7 +826,6 @@ int rwkv_b200_tp_import(rwkv_b200_model *m, const void *ipc_handles) {
         m->p.xch[g] = static_cast<unsigned char *>(ptr);
     }
     m->tp_wired = true;
-    drop_graphs(m);
     return 0;
 }
 

@@ -1,216 +1,35 @@
-// token_kernel.cuh — the persistent one-token kernel: one CTA per SM, launched cooperatively,
-// the whole forward of one token in ONE launch.
+// token_kernel.cuh — the persistent one-token kernel: one CTA per SM, the whole forward of one token
+// in ONE launch, on one GPU or on G GPUs that decode the same stream together.
 //
-// Why (profiles/r01a_staged_ffn_rk_ncu.md): with one kernel per phase, ~45 % of each kernel was the
-// layernorm / token-shift prologue that all 148 CTAs repeated on the same vectors, and the weight
-// stream stopped at every kernel boundary. Here
-//   * each CTA owns a fixed slice of the residual stream (E/grid elements, kept in shared memory
-//     for the whole token) and does the elementwise work for that slice only;
-//   * CTAs exchange the small activation vectors and per-CTA partial reductions through L2, separated
-//     by grid barriers (one monotonic counter, release/acquire at gpu scope);
-//   * the producer warp never waits for a barrier: weights do not depend on activations, so it keeps
-//     filling the shared-memory ring with the NEXT phase's tiles while the consumer warps sit in a
-//     barrier, which keeps HBM busy across phase boundaries.
+// Reference mapping: cuda_rwkv_parralel (include/rwkv/cuda/rwkv.cu:493-593) = embedding + LN0 (513-524),
+// per layer LN1 + mixatt (535-540), K/V/R GEMVs (542), WKV (544-545), out-proj + residual (548-553),
+// LN2 + mixffn (557-562), ffn R/K GEMVs + sigmoid / relu^2 (566-573), ffn V + residual (574-577), then
+// LN_out + head (585-589).
 //
-// Phase structure per layer (B = grid barrier):
-//   [stats -> LN1 + token shift for own slice] B [gather xk,xv,xr; GEMV K,V,R rows of own channels;
-//   WKV for own channels] B [gather rwkv; GEMV out-proj rows; residual for own slice] B
-//   [stats -> LN2 + token shift for own slice] B [gather xr,xk; GEMV ffn-R rows (own slice) and
-//   ffn-K rows; sigmoid / relu^2] B [gather k4; GEMV ffn-V rows; residual for own slice] B
-// then [stats -> LN_out for own slice] B [gather; head GEMV; logits (+ local argmax)] (B [argmax]).
+// Structure
+//   * Each CTA owns a fixed slice of the residual stream (kept in shared memory for the whole token) and
+//     does the elementwise work (layernorm, token shift, WKV, residual adds) for that slice only.
+//   * A producer lane streams this CTA's weight rows HBM -> shared memory through a ring of bulk-TMA tiles.
+//     Weights do not depend on activations, so it never waits for anything but a free ring stage and
+//     keeps HBM busy while the consumer warps exchange vectors.
+//   * Eight consumer warps: warp w takes unit w (one row segment) of every tile, activation limbs in
+//     registers, 12 IDP.4A per 128-bit LDS, REDUX for the exact int32 totals.
+//   * CTAs exchange small vectors as self-tagged words through L2 (exchange.cuh): no grid barrier, no
+//     atomics, a reader proceeds as soon as the words it needs carry the current epoch.
 //
-// Reference mapping is the same as for the staged kernels in kernels.cuh (rwkv.cu:493-593).
+// Dataflow of one layer (-> = tagged exchange inside one GPU, => = partial sums across GPUs, G > 1 only):
+//   slice stats -> [LN1, token shift, own slice] -> xk,xv,xr -> [K,V,R rows of own channels; WKV] -> rwkv
+//   -> [out-proj rows of own slice] => [residual; slice stats] -> [LN2, token shift] -> xr,xk
+//   -> [ffn-R rows of own channels, ffn-K rows; sigmoid, relu^2] -> k4 -> [ffn-V rows of own slice] =>
+//   [residual] ...   then slice stats -> [LN_out] -> xh -> [head rows] -> logits (+ arg-max).
 #pragma once
-#include "kernels.cuh"
+#include "exchange.cuh"
 
 namespace rk {
 
-// ---- thread layout of the token kernel -------------------------------------------------------
-// Eight consumer warps (two per scheduler, each holding the limbs of one n_embed-byte row segment
-// in registers) + one producer warpgroup: its first lane streams the weights, the rest of it only
-// donates registers through setmaxnreg. (Sixteen consumer warps with two warps per row segment
-// and a 104-register budget measured slower: spills.)
 #ifndef RK_CORE_INLINE
 #define RK_CORE_INLINE __forceinline__
 #endif
-#ifndef RK_GATHER_INLINE
-#define RK_GATHER_INLINE __noinline__
-#endif
-constexpr int kTokWarps = 8;                   // one warp per unit of a tile, 232 registers each
-constexpr int kTokConsumers = kTokWarps * 32;
-#ifndef RK_PRODUCER_THREADS
-#define RK_PRODUCER_THREADS 128
-#endif
-// The producer is a whole warpgroup (one lane of it works) so that setmaxnreg can hand its
-// registers to the consumers: 384 threads compile to a budget of 168, consumers then take 232.
-// (A 288-thread CTA does not help: 9 warps put 3 on one scheduler, 16384/96 = 170 registers.)
-// ptxas still makes its pre-allocation choices against 168: left alone it re-derives thread ids,
-// shared-window bases and kernel parameters inside every tile iteration and keeps one shared
-// load in flight (ncu r01d: 45 % of the core's samples). The hot loop therefore takes its
-// operands through opaque() - values the optimiser cannot rematerialise.
-constexpr int kProducerThreads = RK_PRODUCER_THREADS;
-constexpr int kTokThreads = kTokConsumers + kProducerThreads;
-constexpr int kProducerRegs = 40;
-// setmaxnreg budget: the consumers may only take what the producer warpgroup gives back
-// (256 x (232 - 168) = 16384 = 128 x (168 - 40)).
-constexpr int kConsumerRegs = 232;
-
-__device__ __forceinline__ void tok_sync() { // named barrier 1: the eight consumer warps
-    asm volatile("bar.sync 1, %0;" ::"n"(kTokConsumers) : "memory");
-}
-
-// Identity the optimiser cannot see through. The layer loop reads ~35 per-layer arrays at
-// base + l*E + j; left alone, strength reduction turns every one of them into its own 64-bit
-// induction pointer that stays live through the GEMV core (measured: 115 registers live across
-// the core, which then has none left to keep more than one shared-memory load in flight).
-__device__ __forceinline__ int opaque(int v) {
-    asm volatile("" : "+r"(v));
-    return v;
-}
-__device__ __forceinline__ uint32_t opaque(uint32_t v) {
-    asm volatile("" : "+r"(v));
-    return v;
-}
-__device__ __forceinline__ size_t opaque(size_t v) {
-    asm volatile("" : "+l"(v));
-    return v;
-}
-
-// weights (signed bytes) x activation digits (unsigned bytes)
-__device__ __forceinline__ int dp4a_su(uint32_t a, uint32_t b, int c) {
-    int d;
-    asm("dp4a.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-    return d;
-}
-
-// ---- exchange block, peers and scopes -----------------------------------------------------------
-// Everything CTAs exchange lives in ONE allocation per GPU (the "exchange block": barrier counter,
-// accumulators, activation vectors, logits). With tensor parallelism (tp_size ranks, one GPU each)
-// the G GPUs simply form one grid of G*148 CTAs: slices and rows are split over the global CTA
-// index, every publish is stored into the exchange block of EVERY rank (peer-mapped over NVLink,
-// Params::xch[g]), every read is local, and the grid barrier counts the CTAs of all ranks at system
-// scope. tp_size == 1 is the same code with one "peer" (itself) and gpu scope.
-template <class T> __device__ __forceinline__ T *peer_ptr(const Params &p, T *local, int g) {
-    return reinterpret_cast<T *>(p.xch[g] + (reinterpret_cast<unsigned char *>(local) - p.xch[p.tp_rank]));
-}
-__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *ptr, bool sys) {
-    unsigned int v;
-    if (sys) asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
-    else asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
-    return v;
-}
-__device__ __forceinline__ void red_add_u64(unsigned long long *ptr, unsigned long long v, bool sys) {
-    if (sys) asm volatile("red.relaxed.sys.global.add.u64 [%0], %1;" ::"l"(ptr), "l"(v) : "memory");
-    else asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(ptr), "l"(v) : "memory");
-}
-__device__ __forceinline__ void red_max_u64(unsigned long long *ptr, unsigned long long v, bool sys) {
-    if (sys) asm volatile("red.relaxed.sys.global.max.u64 [%0], %1;" ::"l"(ptr), "l"(v) : "memory");
-    else asm volatile("red.relaxed.gpu.global.max.u64 [%0], %1;" ::"l"(ptr), "l"(v) : "memory");
-}
-
-// Accumulators: the per-CTA partial sums / maxima of a phase are combined with integer atomics into
-// a few 64-bit words per rank instead of being published as per-CTA records (G*148 records would
-// cost every reader several L2 round trips). Integer adds commute, so the result is still
-// bit-deterministic. Sums are fixed point (2^-32; sum x^2: 2^-20), maxima are the bit patterns of
-// non-negative doubles (order-preserving as unsigned integers), the arg-max key packs an
-// order-preserving image of the logit above ~index (largest logit, then smallest index, wins).
-// Three buffers rotate with the phase number: written in phase n, read in phase n+1, cleared in
-// phase n+2 by CTA 0 of the owning rank.
-constexpr int kAccSlots = 16;
-constexpr int kAccS1 = 0, kAccS2 = 1, kAccMax = 2, kAccSum = 5, kAccArg = 8;
-__device__ __forceinline__ unsigned long long fx32(double v) {
-    return (unsigned long long)__double2ll_rn(v * 4294967296.0);
-}
-__device__ __forceinline__ double unfx32(unsigned long long u) { return (double)(long long)u * (1.0 / 4294967296.0); }
-__device__ __forceinline__ unsigned long long fx20(double v) {
-    return (unsigned long long)__double2ll_rn(v * 1048576.0);
-}
-__device__ __forceinline__ double unfx20(unsigned long long u) { return (double)(long long)u * (1.0 / 1048576.0); }
-__device__ __forceinline__ unsigned long long *acc_buf(const Params &p, unsigned int phase) {
-    return p.acc + (size_t)(phase % 3u) * kAccSlots;
-}
-
-// Grid barrier over the consumer threads of all CTAs of all ranks (the producer warps do not take
-// part). `phase` = number of barriers completed so far (monotonic across launches, Ctrl::bar_base);
-// it also selects the accumulator buffer. One rank: every CTA adds 1 to gbar and waits for
-// phase*grid. Several ranks, hierarchical: every CTA arrives on the rank-local counter lbar (an
-// acq_rel RMW chain, at system scope so that the CTA's own peer stores are acknowledged first);
-// the last local arriver adds 1 to gbar of EVERY rank; everybody waits for phase*ranks on the own
-// gbar. (Flat all-to-all increments made each counter take ranks*148 remote atomics per barrier:
-// 6.6 us per barrier on 2 GPUs, 14.7 us on 4.)
-// Afterwards CTA 0 clears the accumulator buffer that the phase after next will write.
-__device__ __forceinline__ void grid_sync(const Params &p, unsigned int &phase, int ctid) {
-    tok_sync();
-    ++phase;
-    if (ctid == 0) {
-        unsigned int spins = 0;
-        if (p.tp_size == 1) {
-            // release: everything this CTA wrote (ordered before by the bar.sync above) is visible to
-            // any thread that observes the increment with an acquire load.
-            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.gbar) : "memory");
-            const unsigned int target = phase * gridDim.x;
-            // (polling with relaxed loads and one fence.acq_rel after the loop measured 3 % slower)
-            while ((int)(ld_acquire_u32(p.gbar, false) - target) < 0) {
-                if (++spins > (1u << 25)) __trap();
-            }
-        } else {
-            unsigned int old;
-            asm volatile("atom.acq_rel.sys.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(p.lbar) : "memory");
-            if (old + 1u == phase * gridDim.x) {
-                for (int g = 0; g < p.tp_size; ++g)
-                    asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(peer_ptr(p, p.gbar, g)) : "memory");
-            }
-            const unsigned int target = phase * (unsigned int)p.tp_size;
-            while ((int)(ld_acquire_u32(p.gbar, true) - target) < 0) {
-                if (++spins > (1u << 25)) __trap();
-            }
-        }
-    }
-    tok_sync();
-    if (blockIdx.x == 0 && ctid < kAccSlots) acc_buf(p, phase + 1)[ctid] = 0ull;
-}
-
-// Reductions in the phase-boundary code. Only a few threads ever hold data there (the <= 64 slice
-// owners, the <= 160 row owners, or one lane per CTA partial), and warp shuffles are scarce (one
-// warp-wide SHFL per clock per SM), so nothing here involves all eight warps:
-//   owners_reduce : sum / max over the first `nact` threads; warps without data return at once;
-//                   the participating warps shuffle-reduce and meet at named barrier 2.
-//                   The result is valid in thread 0 only (which publishes it).
-// Deterministic (fixed trees). NS sums then NM maxes (maxes are of non-negative values).
-struct Red {
-    double *buf; // [2][6][8] alternating scratch
-    int par;
-};
-template <int NS, int NM>
-__device__ __forceinline__ void owners_reduce(double *s, double *m, Red &rd, int ctid, int nact) {
-    static_assert(NS + NM <= 6, "reduction scratch holds six values");
-    const int nw = (nact + 31) >> 5;
-    const int w = ctid >> 5;
-    double *b = rd.buf + rd.par * 48;
-    rd.par ^= 1; // every thread toggles on every call, whether or not its warp takes part
-    if (w >= nw) return;
-#pragma unroll
-    for (int k = 0; k < NS; ++k) s[k] = warp_sum(s[k]);
-#pragma unroll
-    for (int k = 0; k < NM; ++k) m[k] = warp_max(m[k]);
-    if (nw > 1) {
-        if ((ctid & 31) == 0) {
-#pragma unroll
-            for (int k = 0; k < NS; ++k) b[k * 8 + w] = s[k];
-#pragma unroll
-            for (int k = 0; k < NM; ++k) b[(NS + k) * 8 + w] = m[k];
-        }
-        asm volatile("bar.sync 2, %0;" ::"r"(nw * 32) : "memory");
-        if (ctid == 0) {
-            for (int i = 1; i < nw; ++i) {
-#pragma unroll
-                for (int k = 0; k < NS; ++k) s[k] += b[k * 8 + i];
-#pragma unroll
-                for (int k = 0; k < NM; ++k) m[k] = fmax(m[k], b[(NS + k) * 8 + i]);
-            }
-        }
-    }
-}
 
 // Position in the shared-memory ring: stage index + parity of the current pass over the ring.
 struct RingPos {
@@ -223,106 +42,112 @@ struct RingPos {
     }
 };
 
-// ---- row-major streaming ---------------------------------------------------------------------
-// Weights are row-major [out][in] int8. A tile is exactly eight work units: a unit is one row
-// segment of SEG = n_embed bytes (rows of E bytes: one unit per row, eight rows per tile; rows of
-// 4E bytes: four units per row, two rows per tile), so consumer warp w always takes unit w of
-// every tile - no dealing logic, no divisions in the loop. The activation limbs of a warp's
-// segment live in its registers (CPL 16-byte chunks per lane x 3 planes).
-// Measured in tools/ringbench.cu (same loop, L2-resident source): 49-52 B/clk/SM, 2.2x the HBM
-// rate; tools/corebench.cu: 64 B/clk/SM for the bare loop. The "lane = row" alternative
-// (activations broadcast from shared memory) is capped at 35-42 B/clk/SM by shared-memory
-// bandwidth - a broadcast LDS.128 still writes 512 B of registers.
-// One issuing lane. Several lanes taking tiles round-robin measured no faster (tools/ringbench.cu)
-// and are unsafe: a lane two ring passes ahead aliases the parity of the empty barrier.
-constexpr int kProducers = 1;
+// Slice ownership of CTA b of nb (per rank). Residual elements are global indices and the same on every
+// rank; channels, key channels and vocabulary rows are relative to the rank's shard.
+struct Slices {
+    int e0, ne; // residual-stream elements = rows of out-proj / ffn-V
+    int c0, nc; // att channels of this rank = rows of K, V, R, ffn-R
+    int k0, nk; // ffn key channels of this rank = rows of ffn-K
+    int v0, nv; // vocabulary rows of this rank
+};
+__host__ __device__ inline void split_rows(int M, int b, int nb, int &r0, int &n) {
+    // M * nb < 2^32 for every matrix here (M <= 50277, nb <= 160): 32-bit unsigned division
+    r0 = (int)(((unsigned int)M * (unsigned int)b) / (unsigned int)nb);
+    n = (int)(((unsigned int)M * (unsigned int)(b + 1)) / (unsigned int)nb) - r0;
+}
+__host__ __device__ inline Slices make_slices(int E, int Er, int Vr, int b, int nb) {
+    Slices s;
+    split_rows(E, b, nb, s.e0, s.ne);
+    split_rows(Er, b, nb, s.c0, s.nc);
+    split_rows(4 * Er, b, nb, s.k0, s.nk);
+    split_rows(Vr, b, nb, s.v0, s.nv);
+    return s;
+}
 
-__device__ __forceinline__ void produce_sub(const Params &p, const Smem &sm, const int8_t *base, int N, int r0, int r1,
-                                            RingPos &rp, uint64_t policy, int &tcount, int pw, unsigned long long *ptrace,
-                                            long long &last_issue) {
-    const uint32_t ring = smem_u32(sm.ring);
-    const uint32_t full0 = smem_u32(sm.full), empty0 = smem_u32(sm.empty);
-    const int tr = (8 * p.E) / N; // rows per tile: 8 (N = E) or 2 (N = 4E)
-    for (int r = r0; r < r1; r += tr) {
-        if ((tcount & (kProducers - 1)) == pw) {
-            const uint32_t bytes = (uint32_t)(min(tr, r1 - r) * N);
-            // first pass over the ring: a fresh mbarrier reports the "previous" phase as complete
-            mbar_wait(empty0 + 8 * rp.stage, rp.phase ^ 1);
-            if (p.issue_gap > 0) {
-                // optional pacing of the bulk copies (set_option "issue_gap", SM cycles): a burst of five
-                // 32 KB tiles at a phase boundary queues ahead of the consumers' latency-critical gather
-                // loads. Measured: 1000 cycles +0.9 % (518 -> 523 tok/s), i.e. not the main effect; off by default.
-                while (clock64() - last_issue < (long long)p.issue_gap) __nanosleep(32);
-                last_issue = clock64();
-            }
-            const uint32_t fb = full0 + 8 * rp.stage;
-            mbar_expect_tx(fb, bytes);
-            bulk_g2s(ring + rp.stage * (uint32_t)p.tile_bytes, base + (size_t)r * N, bytes, fb, policy);
-            if (ptrace != nullptr && tcount < kTileTraceMax) {
-                unsigned long long t;
-                asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-                ptrace[(size_t)blockIdx.x * kTileTraceMax + tcount] = t;
-            }
+// ---- producer ----------------------------------------------------------------------------------------
+// Weights are row-major [out][in] int8. A tile is exactly eight work units; a unit is one row segment
+// (rows of <= E bytes: one unit per row, eight rows per tile; ffn-V rows of 4*Er bytes: four units per
+// row, two rows per tile), so consumer warp w always takes unit w of every tile.
+__device__ __forceinline__ void produce_sub(const Params &p, uint32_t ring, uint32_t full0, uint32_t empty0,
+                                            const int8_t *base, int N, int tr, int r0, int nr, RingPos &rp,
+                                            uint64_t policy, int &tcount, unsigned long long *ptrace, long long &last_issue) {
+    for (int r = 0; r < nr; r += tr) {
+        const uint32_t bytes = (uint32_t)(min(tr, nr - r) * N);
+        // first pass over the ring: a fresh mbarrier reports the "previous" phase as complete
+        mbar_wait(p, empty0 + 8 * rp.stage, rp.phase ^ 1, kDiagRingEmpty);
+        if (p.issue_gap > 0) {
+            while (clock64() - last_issue < (long long)p.issue_gap) __nanosleep(32);
+            last_issue = clock64();
         }
+        const uint32_t fb = full0 + 8 * rp.stage;
+        mbar_expect_tx(fb, bytes);
+        bulk_g2s(ring + rp.stage * (uint32_t)p.tile_bytes, base + (size_t)(r0 + r) * N, bytes, fb, policy);
+        if (ptrace != nullptr && tcount < kTileTraceMax) ptrace[(size_t)blockIdx.x * kTileTraceMax + tcount] = globaltimer();
         ++tcount;
         rp.advance((uint32_t)p.stages);
     }
 }
 
-// Half of a unit's weight bytes -> registers: chunks [HALF*H, HALF*H + H) of the lane.
-template <int H, int HALF, bool FULL>
-__device__ __forceinline__ void load_half(uint4 (&w)[H], uint32_t row, int lane, int nchunks) {
-#pragma unroll
-    for (int i = 0; i < H; ++i) {
-        if (FULL || lane + 32 * (HALF * H + i) < nchunks) w[i] = lds128(row + (HALF * H + i) * 512);
-        else w[i] = make_uint4(0, 0, 0, 0);
+// The producer's whole-token schedule. MUST enumerate subs in exactly the consumers' order.
+template <bool TRACE>
+__device__ __forceinline__ void produce_token(const Params &p, const Smem &sm, const Slices &sl) {
+    unsigned long long *const ptrace = TRACE ? p.ptrace : nullptr;
+    // evict_first keeps the weight stream from displacing the exchange words and the per-layer
+    // parameters in L2 (measured in round 1: evict_normal costs 15 %).
+    const uint64_t pol = policy_evict_first();
+    const int E = p.E, Er = p.Er;
+    const uint32_t ring = smem_u32(sm.ring), full0 = smem_u32(sm.full), empty0 = smem_u32(sm.empty);
+    RingPos rp{0, 0};
+    int tcount = 0;
+    long long last_issue = 0;
+    for (int l = 0; l < p.L_run; ++l) {
+        const size_t mc = (size_t)l * Er * E; // column-split matrices [Er][E]
+        produce_sub(p, ring, full0, empty0, p.wk + mc, E, 8, sl.c0, sl.nc, rp, pol, tcount, ptrace, last_issue);
+        produce_sub(p, ring, full0, empty0, p.wv + mc, E, 8, sl.c0, sl.nc, rp, pol, tcount, ptrace, last_issue);
+        produce_sub(p, ring, full0, empty0, p.wr + mc, E, 8, sl.c0, sl.nc, rp, pol, tcount, ptrace, last_issue);
+        produce_sub(p, ring, full0, empty0, p.wo + mc, Er, 8, sl.e0, sl.ne, rp, pol, tcount, ptrace, last_issue);
+        produce_sub(p, ring, full0, empty0, p.wfr + mc, E, 8, sl.c0, sl.nc, rp, pol, tcount, ptrace, last_issue);
+        produce_sub(p, ring, full0, empty0, p.wfk + 4 * mc, E, 8, sl.k0, sl.nk, rp, pol, tcount, ptrace, last_issue);
+        produce_sub(p, ring, full0, empty0, p.wfv + 4 * mc, 4 * Er, 2, sl.e0, sl.ne, rp, pol, tcount, ptrace, last_issue);
     }
+    produce_sub(p, ring, full0, empty0, p.whead, E, 8, sl.v0, sl.nv, rp, pol, tcount, ptrace, last_issue);
 }
 
-// Exact int32 dot products of half a unit against the three limb planes (two chains per plane).
-template <int CPL, int H, int HALF>
-__device__ __forceinline__ void dot_half(const uint4 (&w)[H], const uint4 (&a0)[CPL], const uint4 (&a1)[CPL],
-                                         const uint4 (&a2)[CPL], int (&acc)[6]) {
-#pragma unroll
-    for (int i = 0; i < H; ++i) {
-        constexpr int o = HALF * H;
-        acc[0] = dp4a_su(w[i].x, a0[o + i].x, acc[0]);
-        acc[2] = dp4a_su(w[i].x, a1[o + i].x, acc[2]);
-        acc[4] = dp4a_ss(w[i].x, a2[o + i].x, acc[4]);
-        acc[1] = dp4a_su(w[i].y, a0[o + i].y, acc[1]);
-        acc[3] = dp4a_su(w[i].y, a1[o + i].y, acc[3]);
-        acc[5] = dp4a_ss(w[i].y, a2[o + i].y, acc[5]);
-        acc[0] = dp4a_su(w[i].z, a0[o + i].z, acc[0]);
-        acc[2] = dp4a_su(w[i].z, a1[o + i].z, acc[2]);
-        acc[4] = dp4a_ss(w[i].z, a2[o + i].z, acc[4]);
-        acc[1] = dp4a_su(w[i].w, a0[o + i].w, acc[1]);
-        acc[3] = dp4a_su(w[i].w, a1[o + i].w, acc[3]);
-        acc[5] = dp4a_ss(w[i].w, a2[o + i].w, acc[5]);
-    }
+// ---- consumer core -----------------------------------------------------------------------------------
+// Exact int32 dot products of one 16-byte chunk against the three limb planes (two chains per plane).
+__device__ __forceinline__ void dot_chunk(const uint4 w, const uint4 a0, const uint4 a1, const uint4 a2, int (&acc)[6]) {
+    acc[0] = dp4a_su(w.x, a0.x, acc[0]);
+    acc[2] = dp4a_su(w.x, a1.x, acc[2]);
+    acc[4] = dp4a_ss(w.x, a2.x, acc[4]);
+    acc[1] = dp4a_su(w.y, a0.y, acc[1]);
+    acc[3] = dp4a_su(w.y, a1.y, acc[3]);
+    acc[5] = dp4a_ss(w.y, a2.y, acc[5]);
+    acc[0] = dp4a_su(w.z, a0.z, acc[0]);
+    acc[2] = dp4a_su(w.z, a1.z, acc[2]);
+    acc[4] = dp4a_ss(w.z, a2.z, acc[4]);
+    acc[1] = dp4a_su(w.w, a0.w, acc[1]);
+    acc[3] = dp4a_su(w.w, a1.w, acc[3]);
+    acc[5] = dp4a_ss(w.w, a2.w, acc[5]);
 }
 
-// Consumer side of one streamed sub-matrix: warp w takes unit w of every tile. All arguments are
-// plain values in registers (the hot loop takes them through opaque(), see above).
-// NSEG = N / E (1 or 4). planes: shared address of limb plane 0 of this sub's activation vector
-// (planes 1, 2 at +N, +2N); res: shared address of this sub's int64 [row][NSEG] partial totals.
-// Variants measured and dropped (gpurun_out A/B of 2026-09-24, 7B shape, tokens/s): this loop 525;
-// all eight loads pinned ahead of the arithmetic with a warp barrier 512; the same as a noinline
-// function 497; software-pipelined in half units (loads of tile t+1 under the arithmetic of tile t,
-// 0.50 instead of 0.64 us per 32 KB tile) as a noinline function 430 - the faster consumer let the
-// producer put 24 MB of bulk copies in flight at every phase boundary and the latency-critical
-// gather loads queued behind them (gather 2.9 -> 6.9 us); inlined it exceeds the register budget.
-template <int CPL, bool FULL, int NSEG>
-__device__ RK_CORE_INLINE RingPos consume_sub(uint32_t ring, uint32_t full0, uint32_t empty0, uint32_t tile_bytes,
-                                            uint32_t stages, uint32_t planes, uint32_t res, int N, int nr, RingPos rp,
-                                            int warp, int lane, unsigned long long *ptrace, int *tile_cnt) {
-    static_assert(CPL % 2 == 0, "chunks per lane must be even");
-    constexpr int TR = 8 / NSEG; // rows per tile
-    constexpr int H = CPL / 2;
-    const int seg_len = N / NSEG;
+// Consumer side of one streamed sub-matrix: warp w takes unit w of every tile. All arguments are plain
+// values in registers (the hot loop takes them through opaque()).
+// N: bytes per row; nseg: segments per row (1 or 4); planes: shared address of limb plane 0 of this sub's
+// activation vector (planes 1, 2 at +N, +2N); res: shared address of this sub's int64 [row][nseg] totals.
+// CPL: 16-byte chunks per lane that hold the limbs of one segment (N / nseg <= CPL * 512).
+// BOUNDED = false: the segment is exactly CPL * 512 bytes - straight-line code, no predicates.
+// BOUNDED = true : any shorter segment (narrow models, the Er-byte rows of a tensor-parallel rank): the
+//                  chunk loop ends at the first chunk index past the segment (a warp-uniform branch).
+template <int CPL, bool BOUNDED>
+__device__ __forceinline__ RingPos consume_sub(const Params &p, uint32_t ring, uint32_t full0, uint32_t empty0, uint32_t tile_bytes,
+                                               uint32_t stages, uint32_t planes, uint32_t res, int N, int nseg, int nr, RingPos rp,
+                                               int warp, int lane, unsigned long long *ptrace, int *tile_cnt) {
+    const int tr = nseg == 4 ? 2 : 8; // rows per tile
+    const int seg_len = nseg == 4 ? N >> 2 : N;
     const int nchunks = seg_len >> 4;
-    const int seg = warp % NSEG, rl = warp / NSEG; // this warp's unit inside every tile
+    const int seg = nseg == 4 ? (warp & 3) : 0, rl = nseg == 4 ? (warp >> 2) : warp; // this warp's unit inside every tile
     const uint32_t unit_off = (uint32_t)(rl * N + seg * seg_len + lane * 16);
-    const int ntiles = (nr + TR - 1) / TR;
+    const int ntiles = (nr + tr - 1) / tr;
     if (ntiles <= 0) return rp;
     uint4 a0[CPL], a1[CPL], a2[CPL];
     {
@@ -330,7 +155,7 @@ __device__ RK_CORE_INLINE RingPos consume_sub(uint32_t ring, uint32_t full0, uin
 #pragma unroll
         for (int i = 0; i < CPL; ++i) {
             const int c = lane + 32 * i;
-            if (FULL || c < nchunks) {
+            if (!BOUNDED || c < nchunks) {
                 a0[i] = lds128(pl + c * 16);
                 a1[i] = lds128(pl + N + c * 16);
                 a2[i] = lds128(pl + 2 * N + c * 16);
@@ -339,27 +164,34 @@ __device__ RK_CORE_INLINE RingPos consume_sub(uint32_t ring, uint32_t full0, uin
             }
         }
     }
-    uint32_t dst = res + (uint32_t)((rl * NSEG + seg) * 8);
+    uint32_t dst = res + (uint32_t)((rl * nseg + seg) * 8);
     int row = rl;
     for (int t = 0; t < ntiles; ++t) {
-        mbar_wait(full0 + 8 * rp.stage, rp.phase);
+        mbar_wait(p, full0 + 8 * rp.stage, rp.phase, kDiagRingFull);
         if (ptrace != nullptr && threadIdx.x == 0) {
             const int c = *tile_cnt;
-            if (c < kTileTraceMax) {
-                unsigned long long tm;
-                asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tm));
-                ptrace[((size_t)gridDim.x + blockIdx.x) * kTileTraceMax + c] = tm;
-            }
+            if (c < kTileTraceMax) ptrace[((size_t)gridDim.x + blockIdx.x) * kTileTraceMax + c] = globaltimer();
             *tile_cnt = c + 1;
         }
         if (row < nr) {
             const uint32_t wrow = ring + rp.stage * tile_bytes + unit_off;
-            uint4 h0[H], h1[H];
-            load_half<H, 0, FULL>(h0, wrow, lane, nchunks);
-            load_half<H, 1, FULL>(h1, wrow, lane, nchunks);
             int acc[6] = {0, 0, 0, 0, 0, 0};
-            dot_half<CPL, H, 0>(h0, a0, a1, a2, acc);
-            dot_half<CPL, H, 1>(h1, a0, a1, a2, acc);
+            if (!BOUNDED) {
+                uint4 w[CPL];
+#pragma unroll
+                for (int i = 0; i < CPL; ++i) w[i] = lds128(wrow + i * 512);
+#pragma unroll
+                for (int i = 0; i < CPL; ++i) dot_chunk(w[i], a0[i], a1[i], a2[i], acc);
+            } else {
+                // chunks of this lane: lane + 32 i < nchunks; whole groups of 32 chunks are warp-uniform
+#pragma unroll
+                for (int i = 0; i < CPL; ++i) {
+                    if (32 * i < nchunks) {
+                        const uint4 w = lane + 32 * i < nchunks ? lds128(wrow + i * 512) : make_uint4(0, 0, 0, 0);
+                        dot_chunk(w, a0[i], a1[i], a2[i], acc);
+                    }
+                }
+            }
             const int t0 = __reduce_add_sync(0xffffffffu, acc[0] + acc[1]);
             const int t1 = __reduce_add_sync(0xffffffffu, acc[2] + acc[3]);
             const int t2 = __reduce_add_sync(0xffffffffu, acc[4] + acc[5]);
@@ -369,7 +201,7 @@ __device__ RK_CORE_INLINE RingPos consume_sub(uint32_t ring, uint32_t full0, uin
             }
         }
         dst += 8 * 8;
-        row += TR;
+        row += tr;
         __syncwarp();
         if (lane == 0) mbar_arrive(empty0 + 8 * rp.stage);
         rp.advance(stages);
@@ -377,268 +209,362 @@ __device__ RK_CORE_INLINE RingPos consume_sub(uint32_t ring, uint32_t full0, uin
     return rp;
 }
 
-// Slice ownership of this CTA.
-struct Slices {
-    int e0, e1, ne; // residual-stream elements / att channels / rows of every E-row matrix
-    int k0, k1, nk; // rows of the 4E-row ffn key matrix
-    int v0, v1, nv; // rows of the head
-};
-__device__ __forceinline__ void split_rows_g(int M, int gb, int gn, int &r0, int &r1) {
-    r0 = (int)(((long long)M * gb) / gn);
-    r1 = (int)(((long long)M * (gb + 1)) / gn);
-}
-// gb / gn: index of this CTA in, and size of, the grid formed by all ranks
-__device__ __forceinline__ Slices make_slices(int E, int gb, int gn) {
-    Slices s;
-    split_rows_g(E, gb, gn, s.e0, s.e1);
-    s.ne = s.e1 - s.e0;
-    split_rows_g(4 * E, gb, gn, s.k0, s.k1);
-    s.nk = s.k1 - s.k0;
-    split_rows_g(kVocab, gb, gn, s.v0, s.v1);
-    s.nv = s.v1 - s.v0;
-    return s;
-}
-
-// The producer's whole-token schedule. MUST enumerate subs in exactly the consumers' order.
-// TRACE: the debug time stamps are compiled in (a separate instantiation: the branches alone cost 2 %).
-template <bool TRACE>
-__device__ __forceinline__ void produce_token(const Params &p, const Smem &sm, const Slices &sl, int pw) {
-    unsigned long long *const ptrace = TRACE ? p.ptrace : nullptr;
-    // evict_first keeps the 7 GB/token weight stream from displacing the exchange vectors and the per-layer
-    // parameters in L2: with evict_normal the same kernel runs at 441 instead of 516 tok/s.
-    const uint64_t pol = policy_evict_first();
-    const int E = p.E;
-    RingPos rp{0, 0};
-    int tcount = 0;
-    long long last_issue = 0;
-    for (int l = 0; l < p.L_run; ++l) {
-        const size_t mo = (size_t)l * E * E;
-        produce_sub(p, sm, p.wk + mo, E, sl.e0, sl.e1, rp, pol, tcount, pw, ptrace, last_issue);
-        produce_sub(p, sm, p.wv + mo, E, sl.e0, sl.e1, rp, pol, tcount, pw, ptrace, last_issue);
-        produce_sub(p, sm, p.wr + mo, E, sl.e0, sl.e1, rp, pol, tcount, pw, ptrace, last_issue);
-        produce_sub(p, sm, p.wo + mo, E, sl.e0, sl.e1, rp, pol, tcount, pw, ptrace, last_issue);
-        produce_sub(p, sm, p.wfr + mo, E, sl.e0, sl.e1, rp, pol, tcount, pw, ptrace, last_issue);
-        produce_sub(p, sm, p.wfk + 4 * mo, E, sl.k0, sl.k1, rp, pol, tcount, pw, ptrace, last_issue);
-        produce_sub(p, sm, p.wfv + 4 * mo, 4 * E, sl.e0, sl.e1, rp, pol, tcount, pw, ptrace, last_issue);
-    }
-    produce_sub(p, sm, p.whead, E, sl.v0, sl.v1, rp, pol, tcount, pw, ptrace, last_issue);
-}
-
-// mean / std of the full residual stream from the accumulated sum(x), sum(x^2), with the
-// reference's f32 rounding of the two accumulators (rwkv.cu:412-465, 43-44).
-// sum((x-m)^2) = s2 - 2 m s1 + E m^2. Every calling lane loads the two words itself (broadcast).
-__device__ __forceinline__ void stats_from_acc(const Params &p, const unsigned long long *acc, double &xmean, double &x2) {
-    const double s1 = unfx32(__ldcg(acc + kAccS1)), s2 = unfx20(__ldcg(acc + kAccS2));
-    const double E = (double)p.E;
-    const float mean_acc = (float)s1;
-    const double mean_f = (double)(mean_acc / (float)p.E);
-    double var = s2 - 2.0 * mean_f * s1 + E * mean_f * mean_f;
-    if (var < 0.0) var = 0.0;
-    const float var_acc = (float)var;
-    xmean = (double)mean_acc / E;
-    x2 = (double)sqrtf(var_acc / (float)(p.E - 1));
-}
-
-// Accumulate this CTA's {sum x, sum x^2} of its slice on every rank.
-__device__ __forceinline__ void publish_stats(const Params &p, const Smem &sm, unsigned int phase, int ne, Red &rd, int ctid) {
-    double s[2] = {0.0, 0.0};
-    if (ctid < ne) {
-        const double v = sm.xown[ctid];
-        s[0] = v;
-        s[1] = v * v;
-    }
-    owners_reduce<2, 0>(s, nullptr, rd, ctid, ne);
-    if (ctid == 0 && ne > 0) {
-        unsigned long long *acc = acc_buf(p, phase);
-        const bool sys = p.tp_size > 1;
-        for (int g = 0; g < p.tp_size; ++g) {
-            unsigned long long *a = peer_ptr(p, acc, g);
-            red_add_u64(a + kAccS1, fx32(s[0]), sys);
-            red_add_u64(a + kAccS2, fx20(s[1]), sys);
-        }
-    }
-}
-
-// Accumulate per-vector {max |xs|, sum x*oc} of this CTA (data in the first `nact` threads).
-template <int NVEC>
-__device__ __forceinline__ void publish_vparts(const Params &p, unsigned int phase, double *mx, double *of, Red &rd,
-                                               int ctid, int nact) {
-    owners_reduce<NVEC, NVEC>(of, mx, rd, ctid, nact);
-    if (ctid == 0 && nact > 0) {
-        unsigned long long *acc = acc_buf(p, phase);
-        const bool sys = p.tp_size > 1;
-        for (int g = 0; g < p.tp_size; ++g) {
-            unsigned long long *a = peer_ptr(p, acc, g);
-#pragma unroll
-            for (int v = 0; v < NVEC; ++v) {
-                red_max_u64(a + kAccMax + v, (unsigned long long)__double_as_longlong(mx[v]), sys);
-                red_add_u64(a + kAccSum + v, fx32(of[v]), sys);
-            }
-        }
-    }
-}
-
-// Activation quantiser of the token kernel: q = round(xs * inv) as a 23-bit two's complement integer
-// (|q| <= 2^22 - 1), and the three limb planes are simply its three low BYTES: bytes 0 and 1 are
-// unsigned digits, byte 2 is the signed top digit, q = b2*65536 + b1*256 + b0. The GEMV uses
-// dp4a.s32.u32 for the two unsigned planes and dp4a.s32.s32 for the signed one (all exact int32).
-// Rounding goes through the float adder (1.5*2^23 + x has ulp 1; the low mantissa bits are the
-// integer) - no F2I, no per-digit bit surgery; four elements are transposed with seven PRMTs.
-constexpr int kQMaxTok = 4194303; // 2^22 - 1
+// ---- activation quantiser -----------------------------------------------------------------------------
+// q = round(xs * inv) as a 23-bit two's complement integer (|q| <= 2^22 - 1); the three limb planes are
+// its three low BYTES: bytes 0 and 1 are unsigned digits, byte 2 is the signed top digit. Rounding goes
+// through the float adder (1.5 * 2^23 + x has ulp 1: the low mantissa bits are the integer) - no F2I;
+// four elements are transposed into the planes with seven PRMTs.
 __device__ __forceinline__ uint32_t round_q(float xs, float inv) {
-    return __float_as_uint(fmaf(xs, inv, 12582912.0f)) - 0x4B400000u; // two's complement q
+    return __float_as_uint(fmaf(xs, inv, 12582912.0f)) - 0x4B400000u;
 }
-__device__ __forceinline__ void quantize4f(const float4 f, float inv, uint8_t *planes, int stride, int j) {
-    const uint32_t t0 = round_q(f.x, inv), t1 = round_q(f.y, inv), t2 = round_q(f.z, inv), t3 = round_q(f.w, inv);
-    const uint32_t lo01 = __byte_perm(t0, t1, 0x5140), lo23 = __byte_perm(t2, t3, 0x5140); // [a.b0,b.b0,a.b1,b.b1]
-    const uint32_t hi01 = __byte_perm(t0, t1, 0x0062), hi23 = __byte_perm(t2, t3, 0x0062); // [a.b2,b.b2,..]
+__device__ __forceinline__ void quantize4(const uint4 f, float inv, uint8_t *planes, int stride, int j) {
+    const uint32_t t0 = round_q(untag_f32(f.x), inv), t1 = round_q(untag_f32(f.y), inv);
+    const uint32_t t2 = round_q(untag_f32(f.z), inv), t3 = round_q(untag_f32(f.w), inv);
+    const uint32_t lo01 = __byte_perm(t0, t1, 0x5140), lo23 = __byte_perm(t2, t3, 0x5140);
+    const uint32_t hi01 = __byte_perm(t0, t1, 0x0062), hi23 = __byte_perm(t2, t3, 0x0062);
     *reinterpret_cast<uint32_t *>(planes + j) = __byte_perm(lo01, lo23, 0x5410);
     *reinterpret_cast<uint32_t *>(planes + stride + j) = __byte_perm(lo01, lo23, 0x7632);
     *reinterpret_cast<uint32_t *>(planes + 2 * stride + j) = __byte_perm(hi01, hi23, 0x5410);
 }
 
-// Debug tracing: thread 0 of each CTA appends %globaltimer to its row of `trace`.
-__device__ __forceinline__ void trace_stamp(unsigned long long *trace, const Smem &sm, int ctid) {
-    if (trace != nullptr && ctid == 0) {
-        int *cnt = reinterpret_cast<int *>(sm.scal + 8);
-        const int c = *cnt;
-        if (c < kTraceMax) {
-            unsigned long long t;
-            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-            trace[(size_t)blockIdx.x * kTraceMax + c] = t;
-            *cnt = c + 1;
-        }
-    }
-}
-
-__device__ __forceinline__ void trace_stamp2(unsigned long long *trace, double *scal, int ctid) {
+// ---- debug tracing --------------------------------------------------------------------------------------
+__device__ __forceinline__ void trace_stamp(unsigned long long *trace, double *scal, int ctid) {
     if (trace != nullptr && ctid == 0) {
         int *cnt = reinterpret_cast<int *>(scal + 8);
         const int c = *cnt;
         if (c < kTraceMax) {
-            unsigned long long t;
-            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-            trace[(size_t)blockIdx.x * kTraceMax + c] = t;
+            trace[(size_t)blockIdx.x * kTraceMax + c] = globaltimer();
             *cnt = c + 1;
         }
     }
 }
 
-// After a barrier: fetch the `nvec` activation vectors of length N (vector v -> limb planes at offset
-// v*3*N) and the accumulated {max |xs|, sum x*oc}, then quantise from registers. All loads (up to
-// 24 x 16 B per thread) are issued before anything is consumed, so the whole gather costs ONE L2
-// round trip; every CTA walks the vector from a different starting offset so that the CTAs do not
-// hit the same L2 lines at the same moment.
-constexpr int kGatherBatches = 6; // x 4 float4 groups x 256 threads x 4 elements >= 4*5120
-__device__ RK_GATHER_INLINE void gather_quantise(uint8_t *planes, double *scal, const float *vec,
-                                             const unsigned long long *acc, int nvec, int N, int ctid, int rot_num,
-                                             int rot_den, unsigned long long *trace) {
-    const int ng = N >> 2;                                             // float4 groups per vector
-    const int nb = (ng + 4 * kTokConsumers - 1) / (4 * kTokConsumers); // batches of 4 groups per thread per vector
-    const int total = nvec * nb;                                       // <= kGatherBatches
-    const int rot = (int)(((long long)ng * rot_num) / rot_den);
-    float4 f[kGatherBatches][4];
+// ---- gather: exchanged vectors -> limb planes --------------------------------------------------------
+// The `nvec` vectors of length N (contiguous f32+tag words at `vec`) were written by their slice owners.
+// Every thread polls the first 16 bytes of its share until they carry this epoch, then fetches the rest
+// in one batch (one L2 round trip when everything has arrived, which is the normal case: the owners
+// publish within a fraction of a microsecond of each other), re-reads whatever was not there yet, takes
+// the per-vector max |xs| over the block and quantises from registers into the limb planes
+// (vector v -> planes + v*3*N). Warp 7 also sums the owners' partial offset sums (OffRec) in a fixed
+// order. Result: scal[v] = S_v (value of one integer step), scal[3+v] = sum_j x_j * oc_j.
+// Every CTA starts at a different offset so that the CTAs do not hit the same L2 lines together.
+// Inlined ONCE (the phase loop of the kernel has a single call site): as a separate function it would be
+// compiled against the 168-register launch budget instead of the consumers' 232 and spill.
+constexpr int kGatherMax = 20; // 16-byte groups per thread: 256 x 20 x 4 >= 4 * 5120
+__device__ __forceinline__ void gather(const Params &p, const Smem &sm, const float *vec, const OffRec *offrec, int nvec,
+                                       int N, uint32_t tag, unsigned int layer, int ctid, unsigned long long *trace) {
+    const uint32_t tag2 = tag & 3u;
+    const int ng = N >> 2;        // groups per vector
+    const int total = nvec * ng;  // <= 256 * kGatherMax
+    const int base = ctid + (int)(((unsigned int)total * blockIdx.x) / gridDim.x);
+    const int cnt = (total - ctid + kConsumers - 1) / kConsumers; // groups of this thread (may be <= 0)
+    const uint4 *src = reinterpret_cast<const uint4 *>(vec);
+    auto index = [&](int i) {
+        int gg = base + kConsumers * i;
+        if (gg >= total) gg -= total;
+        return gg;
+    };
+    const uint4 absent = make_uint4(tag2, tag2, tag2, tag2); // +0.0f carrying the tag: a slot this thread does not have
+    uint4 f[kGatherMax];
+    Waiter wt = waiter_begin();
+    f[0] = absent;
+    if (cnt > 0) {
+        const uint4 *s0 = src + index(0);
+        f[0] = ld_vec4(s0);
+        while (!vec4_ok(f[0], tag2)) {
+            if (waiter_tick(p, wt)) wait_expired(p, kDiagVec, layer, (unsigned int)nvec, tag2, f[0].x & 3u, (unsigned long long)index(0));
+            f[0] = ld_vec4(s0);
+        }
+    }
 #pragma unroll
-    for (int t = 0; t < kGatherBatches; ++t) {
-        if (t < total) {
-            const int v = t / nb, b = t - v * nb;
-            const float4 *src = reinterpret_cast<const float4 *>(vec + (size_t)v * N);
+    for (int i = 1; i < kGatherMax; ++i) {
+        f[i] = absent;
+        if (i < cnt) f[i] = ld_vec4(src + index(i));
+    }
+    // partial offset sums of the owners (warp 7): record r, r+32, ... in ascending order, then a fixed tree
+    if ((ctid >> 5) == kWarps - 1) {
+        const int lane = ctid & 31;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+        for (int r = lane; r < (int)gridDim.x; r += 32) {
+            unsigned long long a0, a1, a2 = 0, a3 = 0, a4 = 0, a5 = 0;
+            for (;;) {
+                ld_pair(&offrec[r].w[0], a0, a1, false);
+                bool ok = tags_ok(a0, a1, tag);
+                if (nvec > 1) {
+                    ld_pair(&offrec[r].w[2], a2, a3, false);
+                    ok = ok && tags_ok(a2, a3, tag);
+                }
+                if (nvec > 2) {
+                    ld_pair(&offrec[r].w[4], a4, a5, false);
+                    ok = ok && tags_ok(a4, a5, tag);
+                }
+                if (ok) break;
+                if (waiter_tick(p, wt)) wait_expired(p, kDiagOff, layer, (unsigned int)nvec, tag, (unsigned int)(a0 >> 32), (unsigned long long)r);
+            }
+            s0 += pair_to_double(a0, a1);
+            if (nvec > 1) s1 += pair_to_double(a2, a3);
+            if (nvec > 2) s2 += pair_to_double(a4, a5);
+        }
+        s0 = warp_sum(s0);
+        s1 = warp_sum(s1);
+        s2 = warp_sum(s2);
+        if (lane == 0) {
+            sm.scal[3] = s0;
+            sm.scal[4] = s1;
+            sm.scal[5] = s2;
+        }
+    }
+    // late words: re-read until every group carries the tag
+    for (;;) {
+        bool bad = false;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int g = ctid + kTokConsumers * (4 * b + k);
-                int gg = g + rot;
-                if (gg >= ng) gg -= ng;
-                f[t][k] = g < ng ? __ldcg(src + gg) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 1; i < kGatherMax; ++i) {
+            if (!vec4_ok(f[i], tag2)) {
+                f[i] = ld_vec4(src + index(i));
+                bad = true;
             }
         }
+        if (!bad) break;
+        if (waiter_tick(p, wt)) wait_expired(p, kDiagVec, layer, (unsigned int)nvec, tag2, 99u, (unsigned long long)base);
     }
-    if (ctid < 3) {
-        double mm = 0.0, ss = 0.0;
-        if (ctid < nvec) {
-            mm = __longlong_as_double((long long)__ldcg(acc + kAccMax + ctid));
-            ss = unfx32(__ldcg(acc + kAccSum + ctid));
-        }
-        scal[ctid] = mm / (double)kQMaxTok;
-        scal[3 + ctid] = ss;
-        reinterpret_cast<float *>(scal + 6)[ctid] = mm > 0.0 ? (float)((double)kQMaxTok / mm) : 0.0f;
+    trace_stamp(trace, sm.scal, ctid); // all words here
+    // per-vector max |xs| (bit patterns of non-negative floats order like unsigned integers)
+    uint32_t mx0 = 0u, mx1 = 0u, mx2 = 0u;
+#pragma unroll
+    for (int i = 0; i < kGatherMax; ++i) {
+        const int gg = index(i);
+        const uint32_t m = max(max(f[i].x & 0x7ffffffcu, f[i].y & 0x7ffffffcu), max(f[i].z & 0x7ffffffcu, f[i].w & 0x7ffffffcu));
+        if (gg < ng) mx0 = max(mx0, m);
+        else if (gg < 2 * ng) mx1 = max(mx1, m);
+        else mx2 = max(mx2, m);
     }
-    trace_stamp2(trace, scal, ctid); // loads issued
+    mx0 = __reduce_max_sync(0xffffffffu, mx0);
+    mx1 = __reduce_max_sync(0xffffffffu, mx1);
+    mx2 = __reduce_max_sync(0xffffffffu, mx2);
+    if ((ctid & 31) == 0) {
+        uint32_t *wm = sm.wmax + (ctid >> 5) * 4;
+        wm[0] = mx0;
+        wm[1] = mx1;
+        wm[2] = mx2;
+    }
     tok_sync();
-    trace_stamp2(trace, scal, ctid); // scales known
     float inv[3];
 #pragma unroll
-    for (int v = 0; v < 3; ++v) inv[v] = reinterpret_cast<const float *>(scal + 6)[v];
+    for (int v = 0; v < 3; ++v) {
+        uint32_t m = 0u;
 #pragma unroll
-    for (int t = 0; t < kGatherBatches; ++t) {
-        if (t < total) {
-            const int v = t / nb, b = t - v * nb;
+        for (int w = 0; w < kWarps; ++w) m = max(m, sm.wmax[w * 4 + v]);
+        const double mm = (double)__uint_as_float(m);
+        inv[v] = mm > 0.0 ? (float)((double)kQMax / mm) : 0.0f;
+        if (ctid == v) sm.scal[v] = mm / (double)kQMax;
+    }
+#pragma unroll
+    for (int i = 0; i < kGatherMax; ++i) {
+        if (i < cnt) {
+            const int gg = index(i);
+            const int v = (gg >= ng) + (gg >= 2 * ng);
             const float iv = v == 0 ? inv[0] : v == 1 ? inv[1] : inv[2];
-            uint8_t *pl = planes + (size_t)v * 3 * N;
+            quantize4(f[i], iv, sm.planes + (size_t)v * 3 * N, N, 4 * (gg - v * ng));
+        }
+    }
+    tok_sync();
+    trace_stamp(trace, sm.scal, ctid); // planes ready
+}
+
+// ---- slice statistics -----------------------------------------------------------------------------------
+// Layernorm statistics of the whole residual stream from per-CTA {sum, M2 = sum (x - slice mean)^2},
+// combined without cancellation: sum_j (x_j - c)^2 = sum_b [M2_b + n_b (mean_b - c)^2] for any c. With
+// c = the reference's f32-rounded mean this is exactly its second pass (rwkv.cu:432-450), and the two
+// accumulators are rounded to f32 like its float atomics (412-465, 43-44). Called by warps 0 and 1
+// (the slice owners); xown holds the slice. Returns mean and sqrt(var) (unbiased, no epsilon).
+__device__ __noinline__ void slice_stats(const Params &p, const Smem &sm, StatRec *recs, int ne, uint32_t tag,
+                                         unsigned int layer, int ctid, double &xmean, double &x2) {
+    own_sync(); // xown complete
+    if (ctid < 32) {
+        const int lane = ctid;
+        const double v0 = lane < ne ? sm.xown[lane] : 0.0, v1 = lane + 32 < ne ? sm.xown[lane + 32] : 0.0;
+        const double s = warp_sum(v0 + v1);
+        const double mb = s / (double)ne;
+        const double d0 = lane < ne ? v0 - mb : 0.0, d1 = lane + 32 < ne ? v1 - mb : 0.0;
+        const double m2 = warp_sum(d0 * d0 + d1 * d1);
+        if (lane == 0) {
+            const unsigned long long us = (unsigned long long)__double_as_longlong(s), um = (unsigned long long)__double_as_longlong(m2);
+            StatRec *mine = recs + blockIdx.x;
+            st_pair(&mine->w[0], tag64((uint32_t)us, tag), tag64((uint32_t)(us >> 32), tag), false);
+            st_pair(&mine->w[2], tag64((uint32_t)um, tag), tag64((uint32_t)(um >> 32), tag), false);
+        }
+        // every CTA's record: r = lane, lane+32, ... ascending, then fixed trees
+        constexpr int kPer = (kMaxGrid + 31) / 32;
+        double sb[kPer], mb2[kPer];
+        double stot = 0.0;
+        Waiter w = waiter_begin();
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int g = ctid + kTokConsumers * (4 * b + k);
-                int gg = g + rot;
-                if (gg >= ng) gg -= ng;
-                if (g < ng) quantize4f(f[t][k], iv, pl, N, 4 * gg);
+        for (int i = 0; i < kPer; ++i) {
+            const int r = lane + 32 * i;
+            sb[i] = 0.0;
+            mb2[i] = 0.0;
+            if (r < (int)gridDim.x) {
+                unsigned long long a, b, c, d;
+                for (;;) {
+                    ld_pair(&recs[r].w[0], a, b, false);
+                    ld_pair(&recs[r].w[2], c, d, false);
+                    if (tags_ok(a, b, tag) && tags_ok(c, d, tag)) break;
+                    if (waiter_tick(p, w)) wait_expired(p, kDiagStats, layer, 0, tag, (unsigned int)(a >> 32), (unsigned long long)r);
+                }
+                sb[i] = pair_to_double(a, b);
+                mb2[i] = pair_to_double(c, d);
+                stot += sb[i];
+            }
+        }
+        stot = warp_sum(stot);
+        const float mean_acc = (float)stot;
+        const double mean_f = (double)(mean_acc / (float)p.E);
+        double q = 0.0;
+#pragma unroll
+        for (int i = 0; i < kPer; ++i) {
+            const int r = lane + 32 * i;
+            if (r < (int)gridDim.x) {
+                int r0, n;
+                split_rows(p.E, r, (int)gridDim.x, r0, n);
+                const double dm = sb[i] / (double)n - mean_f;
+                q += mb2[i] + (double)n * dm * dm;
+            }
+        }
+        q = warp_sum(q);
+        if (lane == 0) {
+            sm.scal[6] = (double)mean_acc / (double)p.E;
+            sm.scal[7] = (double)sqrtf((float)q / (float)(p.E - 1));
+        }
+    }
+    own_sync();
+    xmean = sm.scal[6];
+    x2 = sm.scal[7];
+}
+
+// Partial offset sums of this CTA (data in the first `nact` consumer threads, NV values each) -> its
+// OffRec. Fixed reduction shape: shuffle tree per warp, then warps 0..nw-1 in order. Called by every
+// consumer warp; warps without data return at once. (NV > 1 only for slice owners: <= 2 warps.)
+template <int NV>
+__device__ __forceinline__ void publish_offsums(const Smem &sm, OffRec *recs, double (&of)[NV], uint32_t tag, int ctid, int nact) {
+    const int nw = nact > 0 ? (nact + 31) >> 5 : 1; // an empty slice still publishes zeros
+    const int w = ctid >> 5;
+    if (w >= nw) return;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) of[k] = warp_sum(of[k]);
+    double *scr = sm.scal + 10; // [nw - 1][NV] <= 6 doubles
+    if (nw > 1) {
+        if ((ctid & 31) == 0 && w > 0) {
+#pragma unroll
+            for (int k = 0; k < NV; ++k) scr[(w - 1) * NV + k] = of[k];
+        }
+        asm volatile("bar.sync 3, %0;" ::"r"(nw * 32) : "memory");
+        if (ctid == 0) {
+            for (int i = 1; i < nw; ++i) {
+#pragma unroll
+                for (int k = 0; k < NV; ++k) of[k] += scr[(i - 1) * NV + k];
             }
         }
     }
-    trace_stamp2(trace, scal, ctid); // own quantisation done
-    tok_sync();
+    if (ctid == 0) {
+        OffRec *mine = recs + blockIdx.x;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) st_tagged_double(&mine->w[2 * k], of[k], tag, false);
+    }
 }
 
-// CPL: 16-byte chunks per lane of one n_embed-byte row segment; FULL: n_embed == CPL*512;
+// Sum over the G ranks of the partial result `part` of residual element j (a row-split GEMV): store
+// it into every peer's inbox, wait for the peers' parts, add in rank order (identical on every rank).
+__device__ __noinline__ double peer_sum(const Params &p, unsigned int off_in, int j, double part, uint32_t tag, unsigned int layer) {
+    for (int g = 0; g < p.G; ++g)
+        if (g != p.rank) st_tagged_double(xch_at<TaggedDouble>(p, g, off_in) + ((size_t)p.rank * p.E + j), part, tag, true);
+    double tot = 0.0;
+    const TaggedDouble *in = xch_at<TaggedDouble>(p, p.rank, off_in);
+    Waiter w = waiter_begin();
+    for (int g = 0; g < p.G; ++g) {
+        if (g == p.rank) {
+            tot += part;
+            continue;
+        }
+        unsigned long long a, b;
+        for (;;) {
+            ld_pair(&in[(size_t)g * p.E + j], a, b, true);
+            if (tags_ok(a, b, tag)) break;
+            if (waiter_tick(p, w)) wait_expired(p, kDiagPeerSum, layer, (unsigned int)g, tag, (unsigned int)(a >> 32), (unsigned long long)j);
+        }
+        tot += pair_to_double(a, b);
+    }
+    return tot;
+}
+
+// sigmoid(ffn r) of residual element j, published by the owner of that channel (any rank)
+__device__ __noinline__ float peer_sr(const Params &p, int j, uint32_t tag, unsigned int layer) {
+    const unsigned long long *srp = xch_at<unsigned long long>(p, p.rank, p.off_sr) + j;
+    unsigned long long a;
+    Waiter w = waiter_begin();
+    while ((uint32_t)((a = ld_word(srp, true)) >> 32) != tag) {
+        if (waiter_tick(p, w)) wait_expired(p, kDiagSr, layer, 0, tag, (unsigned int)(a >> 32), (unsigned long long)j);
+    }
+    return __uint_as_float((uint32_t)a);
+}
+
+// CPL: 16-byte chunks per lane of an E-byte row segment; FULL: E == CPL * 512;
 // TRACE: with the %globaltimer stamps of tools/trace_token.py (set_option("trace", 1)).
 template <int CPL, bool FULL, bool TRACE>
-__global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant__ Params p) {
+__global__ void __launch_bounds__(kThreads, 1) k_token(const __grid_constant__ Params p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const Smem sm = carve(smem_raw, p);
     if (threadIdx.x == 0) {
         for (int i = 0; i < p.stages; ++i) {
             mbar_init(smem_u32(&sm.full[i]), 1);
-            mbar_init(smem_u32(&sm.empty[i]), kTokWarps);
+            mbar_init(smem_u32(&sm.empty[i]), kWarps);
         }
         mbar_fence_init();
     }
     __syncthreads();
-    const int E = p.E;
-    const int gn = (int)gridDim.x * p.tp_size, gb = p.tp_rank * (int)gridDim.x + (int)blockIdx.x;
-    const Slices sl = make_slices(E, gb, gn);
+    const int E = p.E, Er = p.Er;
+    const int nb = (int)gridDim.x;
+    const Slices sl = make_slices(E, Er, p.Vr, (int)blockIdx.x, nb);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (warp >= kTokWarps) {
-        if (kProducerThreads == 128) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kProducerRegs));
-        if (lane == 0 && warp - kTokWarps < kProducers) produce_token<TRACE>(p, sm, sl, warp - kTokWarps);
+    if (warp >= kWarps) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kProducerRegs));
+        if (warp == kWarps && lane == 0) produce_token<TRACE>(p, sm, sl);
         return;
     }
-    if (kProducerThreads == 128) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kConsumerRegs));
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kConsumerRegs));
     const int ctid = threadIdx.x;
-    const int ne = sl.ne, nk = sl.nk;
-    const int nwe = (ne + 31) >> 5; // warps that own residual elements
-    Red rd{sm.red, 0};
+    const int ne = sl.ne, nc = sl.nc, nk = sl.nk;
+    const bool owner_warps = warp < 2;  // warps 0 and 1 hold the slice owners (ne, nc <= 64)
+    const bool mine = ctid < ne;        // this thread owns residual element e0 + ctid
+    const bool minec = ctid < nc;       // this thread owns att channel rank*Er + c0 + ctid
+    const bool minek = ctid < nk;       // this thread owns ffn key channel rank*4Er + k0 + ctid
+    const bool multi = p.G > 1;
     if (ctid == 0) {
         *reinterpret_cast<int *>(sm.scal + 8) = 0;
         *reinterpret_cast<int *>(sm.scal + 9) = 0;
     }
     unsigned long long *const c_trace = TRACE ? p.trace : nullptr;
     auto stamp = [&]() {
-        if (TRACE) trace_stamp(c_trace, sm, ctid);
+        if (TRACE) trace_stamp(c_trace, sm.scal, ctid);
     };
-    stamp();
-    const bool mine = ctid < ne;      // this thread owns residual element j
-    const int j0 = sl.e0 + (mine ? ctid : 0);
-    const int j = j0;
-    Ctrl *ctrl = p.ctrl;
-    unsigned int phase = ctrl->bar_base;             // barriers completed so far: phase number, selects the accumulator buffer
+    const int j = sl.e0 + (mine ? ctid : 0);    // residual element (clamped to an owned one)
+    const int cl = sl.c0 + (minec ? ctid : 0);  // channel inside the rank's shard (clamped)
+    const int cg = p.rank * Er + cl;            // global channel
+    const Ctrl *ctrl = p.ctrl;
     unsigned long long token = ctrl->token;
     if (p.feed_mode == 1) token = ctrl->next;
     else if (p.feed_mode == 2) token = p.stream[ctrl->pos];
-    const size_t so0 = (size_t)ctrl->slot * p.L * E; // state slot offset
-    const size_t so = so0;
-    unsigned int q = 0;                              // exchange-buffer parity counter (one per barrier)
-    const bool sys = p.tp_size > 1;
+    const size_t so = (size_t)ctrl->slot * p.L * E; // state slot offset
+    unsigned char *const xl = p.xch[p.rank];
+    StatRec *const stat0 = reinterpret_cast<StatRec *>(xl + p.off_stat[0]);
+    StatRec *const stat1 = reinterpret_cast<StatRec *>(xl + p.off_stat[1]);
+    const double *const saa = reinterpret_cast<const double *>(xl + p.off_saa);
+    const double *const sbb = reinterpret_cast<const double *>(xl + p.off_sbb);
+    double *const pd = sm.pd + (ctid & (kMaxSlice - 1)) * 8; // this owner thread's parameter slots
+    float *const pf = sm.pf + (ctid & (kMaxSlice - 1)) * 8;
+    float *const pk = sm.pk + (ctid < kMaxKeys ? ctid : 0) * 2;
+
     RingPos rp{0, 0};
-    const uint32_t c_ring = opaque(smem_u32(sm.ring)), c_full = opaque(smem_u32(sm.full)),
-                   c_empty = opaque(smem_u32(sm.empty));
+    const uint32_t c_ring = opaque(smem_u32(sm.ring)), c_full = opaque(smem_u32(sm.full)), c_empty = opaque(smem_u32(sm.empty));
     const uint32_t c_planes = opaque(smem_u32(sm.planes)), c_res = opaque(smem_u32(sm.res64));
     const uint32_t c_tile = opaque((uint32_t)p.tile_bytes), c_stages = opaque((uint32_t)p.stages);
     const int c_warp = opaque(warp), c_lane = opaque(lane);
@@ -650,349 +576,393 @@ __global__ void __launch_bounds__(kTokThreads, 1) k_token(const __grid_constant_
         for (int sgm = 0; sgm < nseg; ++sgm) t += sm.res64[off + i * nseg + sgm];
         return (double)t;
     };
-    auto vecp = [&](unsigned int qq) { return p.vec + (size_t)(qq & 1) * 4 * E; };
-    // store one value of a published vector into the exchange block of every rank
-    auto put = [&](float *local, float v) {
-        if (!sys) { *local = v; return; }
-        for (int g = 0; g < p.tp_size; ++g) *peer_ptr(p, local, g) = v;
-    };
+    stamp();
 
-    // ---- x = LN0(emb[token]) for the own slice (rwkv.cu:513-524) --------------------------------
+    // ---- x = LN0(emb[token]) for the own slice (rwkv.cu:513-524): every CTA takes the statistics of the
+    // embedding row itself (two passes with the reference's f32 rounding, rwkv.cu:412-465)
     {
         const float *row = p.emb + (size_t)token * E;
-        auto loadx = [&](int g, double (&v)[4]) {
-            const float4 f = *reinterpret_cast<const float4 *>(row + 4 * g);
-            v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
-        };
-        // two-pass statistics of the embedding row with the reference's f32 rounding (rwkv.cu:412-465)
-        double *sc = sm.red; // [32] scratch: 16 warp sums
+        double *ws = reinterpret_cast<double *>(sm.res64); // res64 is free until the first GEMV
         double sacc = 0.0;
-        for (int g = ctid; g < (E >> 2); g += kTokConsumers) {
-            double v[4];
-            loadx(g, v);
-            sacc += (v[0] + v[1]) + (v[2] + v[3]);
+        for (int g = ctid; g < (E >> 2); g += kConsumers) {
+            const float4 f = *reinterpret_cast<const float4 *>(row + 4 * g);
+            sacc += ((double)f.x + (double)f.y) + ((double)f.z + (double)f.w);
         }
         sacc = warp_sum(sacc);
-        if (lane == 0) sc[warp] = sacc;
+        if (lane == 0) ws[warp] = sacc;
         tok_sync();
         double tot = 0.0;
-        for (int w = 0; w < kTokWarps; ++w) tot += sc[w];
+        for (int w = 0; w < kWarps; ++w) tot += ws[w];
         const float mean_acc = (float)tot;
         const double mean_f = (double)(mean_acc / (float)E);
         double qacc = 0.0;
-        for (int g = ctid; g < (E >> 2); g += kTokConsumers) {
-            double v[4];
-            loadx(g, v);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) qacc += (v[e] - mean_f) * (v[e] - mean_f);
+        for (int g = ctid; g < (E >> 2); g += kConsumers) {
+            const float4 f = *reinterpret_cast<const float4 *>(row + 4 * g);
+            const double d0 = (double)f.x - mean_f, d1 = (double)f.y - mean_f, d2 = (double)f.z - mean_f, d3 = (double)f.w - mean_f;
+            qacc += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
         }
         qacc = warp_sum(qacc);
-        if (lane == 0) sc[16 + warp] = qacc;
+        if (lane == 0) ws[16 + warp] = qacc;
         tok_sync();
         double qtot = 0.0;
-        for (int w = 0; w < kTokWarps; ++w) qtot += sc[16 + w];
+        for (int w = 0; w < kWarps; ++w) qtot += ws[16 + w];
         const double xmean = (double)mean_acc / (double)E;
         const double x2 = (double)sqrtf((float)qtot / (float)(E - 1));
-        tok_sync(); // scratch is reused by owners_reduce below
         if (mine) sm.xown[ctid] = p.ln[j] * (((double)row[j] - xmean) / x2) + p.ln[E + j];
-        publish_stats(p, sm, phase, ne, rd, ctid);
+        tok_sync(); // the scratch in res64 is reused by the first GEMV
     }
-    // parameters of the first LN1 / token-shift slice computation
-    double lw = 0, lb = 0, mk = 0, mv = 0, mr = 0, st = 0;
-    float rk = 0, rv = 0, rr = 0, ok = 0, ov = 0, orr = 0;
-    auto prefetch_att = [&](int l, int j, size_t so) {
-        {   // unconditional (j is clamped to an owned element): a guarded assignment would keep the old
-            // values live through the whole layer and push them into local memory
+
+    // Parameters of the slice computation that follows a residual update, parked in this thread's shared
+    // slots: LN1 + att token shift of layer l (l < L_run), or LN_out + head scale (l == L_run).
+    auto fetch_ln1 = [&](int l) {
+        if (l < p.L_run) {
             const size_t lo = (size_t)l * E + j;
-            lw = p.ln[(size_t)(4 * l + 2) * E + j];
-            lb = p.ln[(size_t)(4 * l + 3) * E + j];
-            mk = p.mixk[lo]; mv = p.mixv[lo]; mr = p.mixr[lo];
-            rk = p.rk[lo]; rv = p.rv[lo]; rr = p.rr[lo];
-            ok = p.ock[lo]; ov = p.ocv[lo]; orr = p.ocr[lo];
-            st = p.sxy[so + lo];
+            cp_async8(pd + 0, p.ln + (size_t)(4 * l + 2) * E + j);
+            cp_async8(pd + 1, p.ln + (size_t)(4 * l + 3) * E + j);
+            cp_async8(pd + 2, p.mixk + lo);
+            cp_async8(pd + 3, p.mixv + lo);
+            cp_async8(pd + 4, p.mixr + lo);
+            cp_async8(pd + 5, p.sxy + so + lo);
+            cp_async4(pf + 0, p.rk + lo);
+            cp_async4(pf + 1, p.rv + lo);
+            cp_async4(pf + 2, p.rr + lo);
+            cp_async4(pf + 3, p.ock + lo);
+            cp_async4(pf + 4, p.ocv + lo);
+            cp_async4(pf + 5, p.ocr + lo);
+        } else {
+            cp_async8(pd + 0, p.ln + (size_t)(4 * p.L + 2) * E + j);
+            cp_async8(pd + 1, p.ln + (size_t)(4 * p.L + 3) * E + j);
+            cp_async4(pf + 0, p.rhead + j);
+            cp_async4(pf + 1, p.ochead + j);
         }
     };
-    if (p.L_run > 0) prefetch_att(0, j0, so0);
-    stamp();
-    grid_sync(p, phase, ctid);
-    stamp();
-    ++q;
-
-    for (int l = 0; l < p.L_run; ++l) {
-        const int j = opaque(j0);
-        const size_t so = opaque(so0);
-        const int lq = opaque(l);
-        const size_t lo = (size_t)lq * E;
-        // ======== LN1 + token shift for the own slice (rwkv.cu:535-540) ==========================
-        {
-            double xmean = 0.0, x2 = 1.0;
-            if (warp < nwe) stats_from_acc(p, acc_buf(p, phase - 1), xmean, x2);
-            double mx[3] = {0, 0, 0}, of[3] = {0, 0, 0};
+    // Slice statistics -> LN1 + token shift of layer l -> publish xk, xv, xr (rwkv.cu:535-540); or, after
+    // the last layer, LN_out -> publish the head input (rwkv.cu:585-588). Warps 0 and 1.
+    auto slice_to_att = [&](int l) {
+        const uint32_t ep = p.ep0 + 1u + (uint32_t)l;
+        double xmean, x2;
+        slice_stats(p, sm, stat0, ne, ep, (unsigned int)l, ctid, xmean, x2);
+        stamp();
+        cp_async_wait();
+        if (l < p.L_run) {
+            float *const vec_kvr = reinterpret_cast<float *>(xl + p.off_vec[0]);
+            double of[3] = {0, 0, 0};
             if (mine) {
-                const double ln = lw * ((sm.xown[ctid] - xmean) * (1.0 / x2)) + lb;
+                const uint32_t t2 = ep & 3u;
+                const double mk = pd[2], mv = pd[3], mr = pd[4], st = pd[5];
+                const double ln = pd[0] * ((sm.xown[ctid] - xmean) * (1.0 / x2)) + pd[1];
                 const float fk = (float)(mk * ln + (1.0 - mk) * st);
                 const float fv = (float)(mv * ln + (1.0 - mv) * st);
                 const float fr = (float)(mr * ln + (1.0 - mr) * st);
-                const float xk = (float)((double)fk * (double)rk);
-                const float xv = (float)((double)fv * (double)rv);
-                const float xr = (float)((double)fr * (double)rr);
-                float *vec = vecp(q);
-                put(vec + j, xk);
-                put(vec + E + j, xv);
-                put(vec + 2 * E + j, xr);
-                mx[0] = fabs((double)xk); mx[1] = fabs((double)xv); mx[2] = fabs((double)xr);
-                of[0] = (double)fk * (double)ok; of[1] = (double)fv * (double)ov; of[2] = (double)fr * (double)orr;
-                p.sxy[so + lo + j] = ln; // only the owner ever reads or writes this element
+                const float xk = (float)((double)fk * (double)pf[0]);
+                const float xv = (float)((double)fv * (double)pf[1]);
+                const float xr = (float)((double)fr * (double)pf[2]);
+                st_f32(vec_kvr + j, tag_f32(xk, t2));
+                st_f32(vec_kvr + E + j, tag_f32(xv, t2));
+                st_f32(vec_kvr + 2 * E + j, tag_f32(xr, t2));
+                of[0] = (double)fk * (double)pf[3];
+                of[1] = (double)fv * (double)pf[4];
+                of[2] = (double)fr * (double)pf[5];
+                p.sxy[so + (size_t)l * E + j] = ln; // only the owner ever reads or writes this element
             }
-            publish_vparts<3>(p, phase, mx, of, rd, ctid, ne);
-        }
-        stamp();
-    grid_sync(p, phase, ctid);
-    stamp();
-        ++q;
-        // ======== K, V, R GEMVs for the own channels + WKV (rwkv.cu:542-545) =====================
-        gather_quantise(sm.planes, sm.scal, vecp(q - 1), acc_buf(p, phase - 1), 3, E, ctid, gb, gn, c_trace);
-        stamp();
-        {
-            double aa = 0, bb = 0, wd = 0, ub = 0, ewd = 0;
-            float ro = 0, oco = 0;
+            publish_offsums<3>(sm, reinterpret_cast<OffRec *>(xl + p.off_off[0]), of, ep, ctid, ne);
+        } else {
+            float *const vec_h = reinterpret_cast<float *>(xl + p.off_vec[4]);
+            double of[1] = {0};
             if (mine) {
-                aa = p.saa[so + lo + j];
-                bb = p.sbb[so + lo + j];
-                wd = p.decay[lo + j];
-                ub = p.bonus[lo + j];
-                ewd = p.expdecay[lo + j];
-                ro = p.ro[lo + j];
-                oco = p.oco[lo + j];
+                const float f = (float)(pd[0] * ((sm.xown[ctid] - xmean) * (1.0 / x2)) + pd[1]);
+                const float xh = (float)((double)f * (double)pf[0]);
+                st_f32(vec_h + j, tag_f32(xh, p.tk & 3u));
+                of[0] = (double)f * (double)pf[1];
+                p.x[j] = sm.xown[ctid]; // residual stream after the last layer (debug / tests)
             }
-            const size_t mo = (size_t)lq * E * E;
-            (void)mo;
-            rp = consume_sub<CPL, FULL, 1>(c_ring, c_full, c_empty, c_tile, c_stages, c_planes + (uint32_t)(0), c_res + (uint32_t)(0) * 8u, E, sl.e1 - sl.e0, rp, c_warp, c_lane, c_ptrace, c_tcnt);
-            rp = consume_sub<CPL, FULL, 1>(c_ring, c_full, c_empty, c_tile, c_stages, c_planes + (uint32_t)(3 * E), c_res + (uint32_t)(ne * 1) * 8u, E, sl.e1 - sl.e0, rp, c_warp, c_lane, c_ptrace, c_tcnt);
-            rp = consume_sub<CPL, FULL, 1>(c_ring, c_full, c_empty, c_tile, c_stages, c_planes + (uint32_t)(6 * E), c_res + (uint32_t)(2 * ne * 1) * 8u, E, sl.e1 - sl.e0, rp, c_warp, c_lane, c_ptrace, c_tcnt);
-            tok_sync();
-            stamp();
-            double mx[3] = {0, 0, 0}, of[3] = {0, 0, 0};
-            if (mine) {
-                const float kf = (float)(sm.scal[0] * row_total(0, ctid, 1) + sm.scal[3]);
-                const float vf = (float)(sm.scal[1] * row_total(ne * 1, ctid, 1) + sm.scal[4]);
-                const float rf = (float)(sm.scal[2] * row_total(2 * ne * 1, ctid, 1) + sm.scal[5]);
-                const double vv = (double)vf;
-                const double e1 = exp(ub + wd + (double)kf);
-                double y = (aa + e1 * vv) / (bb + e1);
-                y = (1.0 / (1.0 + (double)expf(-rf))) * y;
-                const double ek = exp((double)kf), ew = ewd; // exp(decay) is static: tabulated at load
-                p.saa[so + lo + j] = (aa + ek * vv) * ew;
-                p.sbb[so + lo + j] = (bb + ek) * ew;
-                const float rw = (float)y;
-                const float xo = (float)((double)rw * (double)ro);
-                put(vecp(q) + j, xo);
-                mx[0] = fabs((double)xo);
-                of[0] = (double)rw * (double)oco;
-            }
-            publish_vparts<1>(p, phase, mx, of, rd, ctid, ne);
+            publish_offsums<1>(sm, reinterpret_cast<OffRec *>(xl + p.off_off[4]), of, p.tk, ctid, ne);
         }
         stamp();
-    grid_sync(p, phase, ctid);
-    stamp();
-        ++q;
-        // ======== out-projection + residual (rwkv.cu:548-553) =====================================
-        gather_quantise(sm.planes, sm.scal, vecp(q - 1), acc_buf(p, phase - 1), 1, E, ctid, gb, gn, c_trace);
-        stamp();
-        // parameters of the LN2 / ffn token-shift slice computation (used two barriers later)
-        double flw = 0, flb = 0, fmk = 0, fmr = 0, fst = 0;
-        float frr = 0, frk = 0, forr = 0, fok = 0;
-        if (mine) {
-            flw = p.ln[(size_t)(4 * (lq + 1)) * E + j];
-            flb = p.ln[(size_t)(4 * (lq + 1) + 1) * E + j];
-            fmk = p.fmixk[lo + j]; fmr = p.fmixr[lo + j];
-            frr = p.rfr[lo + j]; frk = p.rfk[lo + j];
-            forr = p.ocfr[lo + j]; fok = p.ocfk[lo + j];
-            fst = p.sdd[so + lo + j];
-        }
-        rp = consume_sub<CPL, FULL, 1>(c_ring, c_full, c_empty, c_tile, c_stages, c_planes + (uint32_t)(0), c_res + (uint32_t)(0) * 8u, E, sl.e1 - sl.e0, rp, c_warp, c_lane, c_ptrace, c_tcnt);
-        tok_sync();
-        stamp();
-        if (mine) {
-            const float y = (float)(sm.scal[0] * row_total(0, ctid, 1) + sm.scal[3]);
-            const float xf = (float)sm.xown[ctid] + y;
-            sm.xown[ctid] = (double)xf;
-        }
-        publish_stats(p, sm, phase, ne, rd, ctid);
-        stamp();
-    grid_sync(p, phase, ctid);
-    stamp();
-        ++q;
-        // ======== LN2 + token shift for the own slice (rwkv.cu:557-562) ===========================
-        {
-            double xmean = 0.0, x2 = 1.0;
-            if (warp < nwe) stats_from_acc(p, acc_buf(p, phase - 1), xmean, x2);
-            double mx[3] = {0, 0, 0}, of[3] = {0, 0, 0};
-            if (mine) {
-                const double ln = flw * ((sm.xown[ctid] - xmean) * (1.0 / x2)) + flb;
-                const float fr = (float)(fmr * ln + (1.0 - fmr) * fst);
-                const float fk = (float)(fmk * ln + (1.0 - fmk) * fst);
-                const float xr = (float)((double)fr * (double)frr);
-                const float xk = (float)((double)fk * (double)frk);
-                float *vec = vecp(q);
-                put(vec + j, xr);
-                put(vec + E + j, xk);
-                mx[0] = fabs((double)xr); mx[1] = fabs((double)xk);
-                of[0] = (double)fr * (double)forr; of[1] = (double)fk * (double)fok;
-                p.sdd[so + lo + j] = ln;
-            }
-            publish_vparts<2>(p, phase, mx, of, rd, ctid, ne);
-        }
-        stamp();
-    grid_sync(p, phase, ctid);
-    stamp();
-        ++q;
-        // ======== ffn R (own slice rows) and ffn K (4E rows) + sigmoid / relu^2 (rwkv.cu:566-573) ==
-        gather_quantise(sm.planes, sm.scal, vecp(q - 1), acc_buf(p, phase - 1), 2, E, ctid, gb, gn, c_trace);
-        stamp();
-        {
-            float rvk[2] = {0, 0}, ovk[2] = {0, 0}; // ffn-V scale / offset of the own K rows (<= 2 per thread)
-            const float *rvp = p.rfv + (size_t)lq * 4 * E, *ovp = p.ocfv + (size_t)lq * 4 * E;
-#pragma unroll
-            for (int t = 0; t < 2; ++t) {
-                const int i = ctid + t * kTokConsumers;
-                if (i < nk) {
-                    rvk[t] = rvp[sl.k0 + i];
-                    ovk[t] = ovp[sl.k0 + i];
-                }
-            }
-            rp = consume_sub<CPL, FULL, 1>(c_ring, c_full, c_empty, c_tile, c_stages, c_planes + (uint32_t)(0), c_res + (uint32_t)(0) * 8u, E, sl.e1 - sl.e0, rp, c_warp, c_lane, c_ptrace, c_tcnt);
-            rp = consume_sub<CPL, FULL, 1>(c_ring, c_full, c_empty, c_tile, c_stages, c_planes + (uint32_t)(3 * E), c_res + (uint32_t)(ne * 1) * 8u, E, sl.k1 - sl.k0, rp, c_warp, c_lane, c_ptrace, c_tcnt);
-            tok_sync();
-            stamp();
-            if (mine) {
-                const float y = (float)(sm.scal[0] * row_total(0, ctid, 1) + sm.scal[3]);
-                sm.srown[ctid] = (float)(1.0 / (1.0 + exp(-(double)y)));
-            }
-            double mx[3] = {0, 0, 0}, of[3] = {0, 0, 0};
-            float *vec = vecp(q);
-#pragma unroll
-            for (int t = 0; t < 2; ++t) {
-                const int i = ctid + t * kTokConsumers;
-                if (i < nk) {
-                    float a = (float)(sm.scal[1] * row_total(ne * 1, i, 1) + sm.scal[4]);
-                    a = a > 0.0f ? a : 0.0f;
-                    a = a * a;
-                    const float xv = (float)((double)a * (double)rvk[t]);
-                    put(vec + sl.k0 + i, xv);
-                    mx[0] = fmax(mx[0], (double)xv);
-                    of[0] += (double)a * (double)ovk[t];
-                }
-            }
-            publish_vparts<1>(p, phase, mx, of, rd, ctid, nk < kRedMax ? nk : kRedMax);
-        }
-        stamp();
-    grid_sync(p, phase, ctid);
-    stamp();
-        ++q;
-        // ======== ffn V (rows of 4E bytes, four warps per row) + residual (rwkv.cu:574-577) =========
-        gather_quantise(sm.planes, sm.scal, vecp(q - 1), acc_buf(p, phase - 1), 1, 4 * E, ctid, gb, gn, c_trace);
-        stamp();
-        rp = consume_sub<CPL, FULL, 4>(c_ring, c_full, c_empty, c_tile, c_stages, c_planes + (uint32_t)(0), c_res + (uint32_t)(0) * 8u, 4 * E, sl.e1 - sl.e0, rp, c_warp, c_lane, c_ptrace, c_tcnt);
-        // issued after the register-hungry core; the loads land during the epilogue + grid barrier
-        if (l + 1 < p.L_run) prefetch_att(lq + 1, j, so);
-        tok_sync();
-        stamp();
-        if (mine) {
-            const float kv = (float)(sm.scal[0] * row_total(0, ctid, 4 * 1) + sm.scal[3]);
-            sm.xown[ctid] = sm.xown[ctid] + (double)(kv * sm.srown[ctid]);
-        }
-        publish_stats(p, sm, phase, ne, rd, ctid);
-        stamp();
-    grid_sync(p, phase, ctid);
-    stamp();
-        ++q;
+    };
+    if (owner_warps) {
+        fetch_ln1(0);
+        slice_to_att(0);
     }
 
-    // ======== LN_out for the own slice, head GEMV (rwkv.cu:585-589) ================================
-    {
-        double xmean = 0.0, x2 = 1.0;
-        if (warp < nwe) stats_from_acc(p, acc_buf(p, phase - 1), xmean, x2);
-        double mx[3] = {0, 0, 0}, of[3] = {0, 0, 0};
-        if (mine) {
-            const double *lwp = p.ln + (size_t)(4 * p.L + 2) * E;
-            const float f = (float)(lwp[j] * ((sm.xown[ctid] - xmean) * (1.0 / x2)) + lwp[E + j]);
-            const float xh = (float)((double)f * (double)p.rhead[j]);
-            put(vecp(q) + j, xh);
-            mx[0] = fabs((double)xh);
-            of[0] = (double)f * (double)p.ochead[j];
-            p.x[j] = sm.xown[ctid]; // residual stream after the last layer (debug / tests)
+    // ---- the phase loop: 4 phases per layer, then the head. One call site each for the gather and the
+    // GEMV core keeps the layer body small enough for the instruction cache.
+    const int n_iter = 4 * p.L_run + 1;
+    for (int it = 0; it < n_iter; ++it) {
+        const int itq = opaque(it);
+        const int l = itq >> 2;
+        const int ph = itq == 4 * p.L_run ? 4 : (itq & 3);
+        const size_t lo = (size_t)l * E;
+        const uint32_t ep = p.ep0 + 1u + (uint32_t)l;
+        // -------- what this phase gathers and streams ---------------------------------------------
+        int nvec, N, nseg, nsub, nr0, nr1;
+        uint32_t tag;
+        switch (ph) {
+        case 0: nvec = 3; N = E; nseg = 1; nsub = 3; nr0 = nc; nr1 = nc; tag = ep; break;           // K, V, R
+        case 1: nvec = 1; N = Er; nseg = 1; nsub = 1; nr0 = ne; nr1 = 0; tag = ep; break;           // out-proj
+        case 2: nvec = 2; N = E; nseg = 1; nsub = 2; nr0 = nc; nr1 = nk; tag = ep; break;           // ffn R, ffn K
+        case 3: nvec = 1; N = 4 * Er; nseg = 4; nsub = 1; nr0 = ne; nr1 = 0; tag = ep; break;       // ffn V
+        default: nvec = 1; N = E; nseg = 1; nsub = 1; nr0 = sl.nv; nr1 = 0; tag = p.tk; break;      // head
         }
-        publish_vparts<1>(p, phase, mx, of, rd, ctid, ne);
-    }
-    stamp();
-    grid_sync(p, phase, ctid);
-    stamp();
-    ++q;
-    gather_quantise(sm.planes, sm.scal, vecp(q - 1), acc_buf(p, phase - 1), 1, E, ctid, gb, gn, c_trace);
-    stamp();
-    rp = consume_sub<CPL, FULL, 1>(c_ring, c_full, c_empty, c_tile, c_stages, c_planes + (uint32_t)(0), c_res + (uint32_t)(0) * 8u, E, sl.v1 - sl.v0, rp, c_warp, c_lane, c_ptrace, c_tcnt);
-    tok_sync();
-    stamp();
-    {
-        float best = -INFINITY;
-        int bidx = 0x7fffffff;
-        for (int i = ctid; i < sl.nv; i += kTokConsumers) {
-            const float y = (float)(sm.scal[0] * row_total(0, i, 1) + sm.scal[3]);
-            put(p.logits + sl.v0 + i, y);
-            if (y > best) { // i ascending per thread: first maximum kept
-                best = y;
-                bidx = sl.v0 + i;
+        const float *vec = reinterpret_cast<const float *>(xl + p.off_vec[ph]);
+        const OffRec *offrec = reinterpret_cast<const OffRec *>(xl + p.off_off[ph]);
+        // -------- park the epilogue's parameters in shared memory ------------------------------------
+        if (ph == 0) {
+            if (owner_warps) { // WKV of channel cg (clamped: an idle thread reads a valid address)
+                cp_async8(pd + 0, saa + so + lo + cg);
+                cp_async8(pd + 1, sbb + so + lo + cg);
+                cp_async8(pd + 2, p.decay + lo + cg);
+                cp_async8(pd + 3, p.bonus + lo + cg);
+                cp_async8(pd + 4, p.expdecay + lo + cg);
+                cp_async4(pf + 0, p.ro + lo + cg);
+                cp_async4(pf + 1, p.oco + lo + cg);
+            }
+        } else if (ph == 1) {
+            if (owner_warps) { // LN2 + ffn token shift of element j
+                cp_async8(pd + 0, p.ln + (size_t)(4 * (l + 1)) * E + j);
+                cp_async8(pd + 1, p.ln + (size_t)(4 * (l + 1) + 1) * E + j);
+                cp_async8(pd + 2, p.fmixk + lo + j);
+                cp_async8(pd + 3, p.fmixr + lo + j);
+                cp_async8(pd + 4, p.sdd + so + lo + j);
+                cp_async4(pf + 0, p.rfr + lo + j);
+                cp_async4(pf + 1, p.rfk + lo + j);
+                cp_async4(pf + 2, p.ocfr + lo + j);
+                cp_async4(pf + 3, p.ocfk + lo + j);
+            }
+        } else if (ph == 2) {
+            if (minek) { // ffn-V scale / offset of the own key channel
+                const size_t ko = (size_t)l * 4 * E + (size_t)p.rank * 4 * Er + sl.k0 + ctid;
+                cp_async4(pk + 0, p.rfv + ko);
+                cp_async4(pk + 1, p.ocfv + ko);
+            }
+        } else if (ph == 3) {
+            if (owner_warps) fetch_ln1(l + 1);
+        }
+        // -------- gather + stream ------------------------------------------------------------------
+        gather(p, sm, vec, offrec, nvec, N, tag, (unsigned int)l, ctid, c_trace);
+        {
+            const bool exact = FULL && N == (nseg == 4 ? 4 * E : E); // segment == CPL * 512 bytes
+            uint32_t planes = c_planes, res = c_res;
+            for (int s = 0; s < nsub; ++s) {
+                const int nr = s == 0 ? nr0 : (ph == 0 ? nr0 : nr1);
+                if (exact) rp = consume_sub<CPL, false>(p, c_ring, c_full, c_empty, c_tile, c_stages, planes, res, N, nseg, nr, rp, c_warp, c_lane, c_ptrace, c_tcnt);
+                else rp = consume_sub<CPL, true>(p, c_ring, c_full, c_empty, c_tile, c_stages, planes, res, N, nseg, nr, rp, c_warp, c_lane, c_ptrace, c_tcnt);
+                planes += (uint32_t)(3 * N);
+                res += (uint32_t)(nr * nseg) * 8u;
             }
         }
-        if (p.greedy) {
-            // block arg-max, first index wins ties
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const float ov2 = __shfl_xor_sync(0xffffffffu, best, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
-                if (ov2 > best || (ov2 == best && oi < bidx)) {
-                    best = ov2;
-                    bidx = oi;
-                }
-            }
-            float *bv = reinterpret_cast<float *>(sm.red);
-            int *bi = reinterpret_cast<int *>(sm.red + 16);
-            tok_sync();
-            if (lane == 0) {
-                bv[warp] = best;
-                bi[warp] = bidx;
-            }
-            tok_sync();
-            if (ctid == 0) {
-                for (int w = 1; w < kTokWarps; ++w)
-                    if (bv[w] > best || (bv[w] == best && bi[w] < bidx)) {
-                        best = bv[w];
-                        bidx = bi[w];
+        tok_sync();
+        stamp();
+        cp_async_wait();
+        // -------- epilogue ----------------------------------------------------------------------------
+        if (ph == 0) {
+            // ======== WKV for the own channels (rwkv.cu:544-545) -> rwkv * r_out =========================
+            if (owner_warps) {
+                double of[1] = {0};
+                if (minec) {
+                    const double aa = pd[0], bb = pd[1], wd = pd[2], ub = pd[3], ew = pd[4]; // exp(decay) is static: tabulated at load
+                    const float kf = (float)(sm.scal[0] * row_total(0, ctid, 1) + sm.scal[3]);
+                    const float vf = (float)(sm.scal[1] * row_total(nc, ctid, 1) + sm.scal[4]);
+                    const float rf = (float)(sm.scal[2] * row_total(2 * nc, ctid, 1) + sm.scal[5]);
+                    const double vv = (double)vf;
+                    const double e1 = exp(ub + wd + (double)kf);
+                    double y = (aa + e1 * vv) / (bb + e1);
+                    y = (1.0 / (1.0 + (double)expf(-rf))) * y;
+                    const double ek = exp((double)kf);
+                    const double naa = (aa + ek * vv) * ew, nbb = (bb + ek) * ew;
+                    // every rank keeps the WKV state of all channels (plain peer stores, ordered before the
+                    // completion flags at the end of the kernel)
+                    for (int g = 0; g < p.G; ++g) {
+                        xch_at<double>(p, g, p.off_saa)[so + lo + cg] = naa;
+                        xch_at<double>(p, g, p.off_sbb)[so + lo + cg] = nbb;
                     }
-                if (bidx != 0x7fffffff) {
-                    // order-preserving image of the float above ~index: max = largest logit, then smallest index
-                    unsigned int u = __float_as_uint(best);
-                    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-                    const unsigned long long key = ((unsigned long long)u << 32) | (unsigned long long)(0xffffffffu - (unsigned int)bidx);
-                    unsigned long long *acc = acc_buf(p, phase);
-                    for (int g = 0; g < p.tp_size; ++g) red_max_u64(peer_ptr(p, acc, g) + kAccArg, key, sys);
+                    const float rw = (float)y;
+                    const float xo = (float)((double)rw * (double)pf[0]);
+                    st_f32(reinterpret_cast<float *>(xl + p.off_vec[1]) + cl, tag_f32(xo, ep & 3u));
+                    of[0] = (double)rw * (double)pf[1];
+                }
+                publish_offsums<1>(sm, reinterpret_cast<OffRec *>(xl + p.off_off[1]), of, ep, ctid, nc);
+            }
+        } else if (ph == 1) {
+            // ======== residual (rwkv.cu:548-553), then LN2 + token shift (557-562) ========================
+            if (owner_warps) {
+                if (mine) {
+                    double part = sm.scal[0] * row_total(0, ctid, 1) + sm.scal[3];
+                    if (multi) part = peer_sum(p, p.off_in[0], j, part, ep, (unsigned int)l);
+                    const float y = (float)part;
+                    const float xf = (float)sm.xown[ctid] + y; // the reference accumulates on an f32 copy of x
+                    sm.xown[ctid] = (double)xf;
+                }
+                stamp();
+                double xmean, x2;
+                slice_stats(p, sm, stat1, ne, ep, (unsigned int)l, ctid, xmean, x2);
+                stamp();
+                double of[2] = {0, 0};
+                if (mine) {
+                    const double fmk = pd[2], fmr = pd[3], fst = pd[4];
+                    const double ln = pd[0] * ((sm.xown[ctid] - xmean) * (1.0 / x2)) + pd[1];
+                    const float fr = (float)(fmr * ln + (1.0 - fmr) * fst);
+                    const float fk = (float)(fmk * ln + (1.0 - fmk) * fst);
+                    const float xr = (float)((double)fr * (double)pf[0]);
+                    const float xk = (float)((double)fk * (double)pf[1]);
+                    float *const vec_rk = reinterpret_cast<float *>(xl + p.off_vec[2]);
+                    st_f32(vec_rk + j, tag_f32(xr, ep & 3u));
+                    st_f32(vec_rk + E + j, tag_f32(xk, ep & 3u));
+                    of[0] = (double)fr * (double)pf[2];
+                    of[1] = (double)fk * (double)pf[3];
+                    p.sdd[so + lo + j] = ln;
+                }
+                publish_offsums<2>(sm, reinterpret_cast<OffRec *>(xl + p.off_off[2]), of, ep, ctid, ne);
+            }
+        } else if (ph == 2) {
+            // ======== sigmoid(ffn r) for the own channels, relu^2 of the own key channels (566-573) =======
+            if (minec) {
+                const float y = (float)(sm.scal[0] * row_total(0, ctid, 1) + sm.scal[3]);
+                const float sr = (float)(1.0 / (1.0 + exp(-(double)y)));
+                if (!multi) sm.srown[ctid] = sr; // one GPU: channel owner == residual owner
+                else
+                    for (int g = 0; g < p.G; ++g) st_word(xch_at<unsigned long long>(p, g, p.off_sr) + cg, tag64(__float_as_uint(sr), ep), true);
+            }
+            double of[1] = {0};
+            if (minek) {
+                float a = (float)(sm.scal[1] * row_total(nc, ctid, 1) + sm.scal[4]);
+                a = a > 0.0f ? a : 0.0f;
+                a = a * a;
+                const float xv = (float)((double)a * (double)pk[0]);
+                st_f32(reinterpret_cast<float *>(xl + p.off_vec[3]) + sl.k0 + ctid, tag_f32(xv, ep & 3u));
+                of[0] = (double)a * (double)pk[1];
+            }
+            publish_offsums<1>(sm, reinterpret_cast<OffRec *>(xl + p.off_off[3]), of, ep, ctid, nk);
+        } else if (ph == 3) {
+            // ======== residual (rwkv.cu:574-577), then the next layer's LN1 (or LN_out) ====================
+            if (owner_warps) {
+                if (mine) {
+                    double part = sm.scal[0] * row_total(0, ctid, 4) + sm.scal[3];
+                    float sr;
+                    if (multi) {
+                        part = peer_sum(p, p.off_in[1], j, part, ep, (unsigned int)l);
+                        sr = peer_sr(p, j, ep, (unsigned int)l);
+                    } else {
+                        sr = sm.srown[ctid];
+                    }
+                    const float kv = (float)part;
+                    sm.xown[ctid] = sm.xown[ctid] + (double)(kv * sr);
+                }
+                stamp();
+                slice_to_att(l + 1);
+            }
+        } else {
+            // ======== logits (rwkv.cu:589), arg-max =====================================================
+            float best = -INFINITY;
+            int bidx = 0x7fffffff;
+            for (int i = ctid; i < sl.nv; i += kConsumers) {
+                const float y = (float)(sm.scal[0] * row_total(0, i, 1) + sm.scal[3]);
+                const int vi = p.vbase + sl.v0 + i;
+                for (int g = 0; g < p.G; ++g) xch_at<float>(p, g, p.off_logits)[vi] = y;
+                if (y > best) { // i ascending per thread: first maximum kept
+                    best = y;
+                    bidx = vi;
                 }
             }
-            stamp();
-    grid_sync(p, phase, ctid);
-    stamp();
-            if (blockIdx.x == 0 && ctid == 0) {
-                const unsigned long long key = __ldcg(acc_buf(p, phase - 1) + kAccArg);
-                const unsigned int ix = 0xffffffffu - (unsigned int)(key & 0xffffffffull);
-                ctrl->next = (unsigned long long)(key == 0ull ? 0u : ix);
+            if (p.greedy) {
+                // block arg-max, first index wins ties
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float ov2 = __shfl_xor_sync(0xffffffffu, best, o);
+                    const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+                    if (ov2 > best || (ov2 == best && oi < bidx)) {
+                        best = ov2;
+                        bidx = oi;
+                    }
+                }
+                float *bv = reinterpret_cast<float *>(sm.wmax);
+                int *bi = reinterpret_cast<int *>(sm.wmax + 8);
+                if (lane == 0) {
+                    bv[warp] = best;
+                    bi[warp] = bidx;
+                }
+                tok_sync();
+                if (ctid == 0) {
+                    for (int w = 1; w < kWarps; ++w)
+                        if (bv[w] > best || (bv[w] == best && bi[w] < bidx)) {
+                            best = bv[w];
+                            bidx = bi[w];
+                        }
+                    for (int g = 0; g < p.G; ++g)
+                        st_pair(xch_at<TaggedDouble>(p, g, p.off_arg) + ((size_t)p.rank * nb + blockIdx.x),
+                                tag64(__float_as_uint(best), p.tk), tag64((uint32_t)bidx, p.tk), multi);
+                }
+                if (blockIdx.x == 0) {
+                    // CTA 0 of every rank picks the winner of all G x nb candidates (same result everywhere)
+                    const TaggedDouble *cand = xch_at<TaggedDouble>(p, p.rank, p.off_arg);
+                    float b2 = -INFINITY;
+                    int i2 = 0x7fffffff;
+                    Waiter w = waiter_begin();
+                    for (int r = ctid; r < p.G * nb; r += kConsumers) {
+                        unsigned long long a, b;
+                        for (;;) {
+                            ld_pair(&cand[r], a, b, multi);
+                            if (tags_ok(a, b, p.tk)) break;
+                            if (waiter_tick(p, w)) wait_expired(p, kDiagArg, (unsigned int)l, 0, p.tk, (unsigned int)(a >> 32), (unsigned long long)r);
+                        }
+                        const float v = __uint_as_float((uint32_t)a);
+                        const int ix = (int)(uint32_t)b;
+                        if (v > b2 || (v == b2 && ix < i2)) {
+                            b2 = v;
+                            i2 = ix;
+                        }
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const float ov2 = __shfl_xor_sync(0xffffffffu, b2, o);
+                        const int oi = __shfl_xor_sync(0xffffffffu, i2, o);
+                        if (ov2 > b2 || (ov2 == b2 && oi < i2)) {
+                            b2 = ov2;
+                            i2 = oi;
+                        }
+                    }
+                    tok_sync(); // bv / bi of the first reduction are consumed
+                    if (lane == 0) {
+                        bv[warp] = b2;
+                        bi[warp] = i2;
+                    }
+                    tok_sync();
+                    if (ctid == 0) {
+                        for (int w2 = 1; w2 < kWarps; ++w2)
+                            if (bv[w2] > b2 || (bv[w2] == b2 && bi[w2] < i2)) {
+                                b2 = bv[w2];
+                                i2 = bi[w2];
+                            }
+                        p.ctrl->next = (unsigned long long)(i2 == 0x7fffffff ? 0 : i2);
+                    }
+                }
             }
         }
+        stamp();
     }
-    if (blockIdx.x == 0 && ctid == 0) {
-        ctrl->bar_base = phase;
-        if (p.feed_mode == 2) ctrl->pos = ctrl->pos + 1;
+    if (multi) {
+        // Everything this CTA stored into the peers (logits rows, WKV state) must have landed before any
+        // rank's kernel completes: fence, then a completion flag to CTA b of every rank, then wait for the
+        // flags of the peers' CTA b.
+        __threadfence_system();
+        tok_sync();
+        if (ctid == 0) {
+            __threadfence_system();
+            for (int g = 0; g < p.G; ++g)
+                st_word(xch_at<unsigned long long>(p, g, p.off_done) + ((size_t)p.rank * nb + blockIdx.x), tag64(1u, p.tk), true);
+        }
+        if (ctid < p.G) {
+            const unsigned long long *d = xch_at<unsigned long long>(p, p.rank, p.off_done) + ((size_t)ctid * nb + blockIdx.x);
+            unsigned long long a;
+            Waiter w = waiter_begin();
+            while ((uint32_t)((a = ld_word(d, true)) >> 32) != p.tk) {
+                if (waiter_tick(p, w)) wait_expired(p, kDiagDone, (unsigned int)p.L_run, (unsigned int)ctid, p.tk, (unsigned int)(a >> 32), 0ull);
+            }
+            __threadfence_system();
+        }
     }
+    if (blockIdx.x == 0 && ctid == 0 && p.feed_mode == 2) p.ctrl->pos = p.ctrl->pos + 1;
+    stamp();
 }
 
 } // namespace rk

@@ -177,9 +177,7 @@ class Engine:
 
     def debug_read(self, name):
         E = self.n_embed
-        dt, n = {"x": (np.float64, E), "xy_new": (np.float64, E), "dd_new": (np.float64, E),
-                 "xs_o": (np.float32, E), "sr": (np.float32, E), "xs_v": (np.float32, 4 * E),
-                 "logits": (np.float32, VOCAB)}[name]
+        dt, n = {"x": (np.float64, E), "logits": (np.float32, VOCAB)}[name]
         a = np.empty(n, dt)
         got = self.lib.rwkv_b200_debug_read(self.h, name.encode(), a.ctypes.data_as(ctypes.c_void_p), a.nbytes)
         if got != n:
@@ -196,11 +194,11 @@ class Engine:
 
     def read_tile_trace(self, grid=148, per_cta=4096):
         """[2][grid][per_cta] globaltimer: tile copy issued by the producer / tile seen ready by consumer thread 0."""
-        a = np.zeros(3 * grid * per_cta, np.uint64)
+        a = np.zeros(2 * grid * per_cta, np.uint64)
         got = self.lib.rwkv_b200_debug_read(self.h, b"ptrace", a.ctypes.data_as(ctypes.c_void_p), a.nbytes)
         if got != a.size:
             raise EngineError("read_tile_trace failed")
-        return a.reshape(3, grid, per_cta)
+        return a.reshape(2, grid, per_cta)
 
     def decode_timed(self, tokens, teacher_forced=True):
         toks = np.ascontiguousarray(np.asarray(tokens, dtype=np.uint64))

@@ -1,5 +1,5 @@
-"""Phase-level timing of the persistent token kernel from %globaltimer stamps.
-usage: python trace_token.py [workload=7b]"""
+"""Phase-level timing of the persistent token kernel from %globaltimer stamps (thread 0 of every CTA).
+usage: python trace_token.py [workload=7b] [tokens=4]"""
 import importlib
 import os
 import sys
@@ -12,11 +12,12 @@ import bench  # noqa: E402
 
 pkg = importlib.import_module("rwkv-cpp-accelerated_b200")
 workload = sys.argv[1] if len(sys.argv) > 1 else "7b"
+ntok = int(sys.argv[2]) if len(sys.argv) > 2 else 4
 L, E = bench.SHAPES[workload]
 eng = pkg.Engine(bench.model_path(workload, pkg))
 eng.set_option("trace", 1)
 tok = bench.SEED_TOKEN
-for _ in range(4):
+for _ in range(ntok):
     tok = eng.forward_greedy(tok)
 tr = eng.read_trace().astype(np.int64)
 n = int((tr[0] > 0).sum())
@@ -24,49 +25,47 @@ tr = tr[:, :n]
 t0 = tr[:, 0].min()
 tr = tr - t0
 print("stamps per CTA", n, "token time us", (tr[:, -1].max()) / 1e3)
-# stamp layout: 0 start | 1 E(embed) 2 B | per layer: [slice: E B][kvr: G C E B][out: G C E B][ffn slice: E B][rk: G C E B][v: G C E B] | head...
-names = []
-names += ["embed.epi", "embed.bar"]
-for l in range(L):
-    for ph in ("kvr", "out", "rk", "v"):
-        if ph in ("kvr", "rk"):
-            names += [("att_ln" if ph == "kvr" else "ffn_ln") + ".epi", ("att_ln" if ph == "kvr" else "ffn_ln") + ".bar"]
-        names += [ph + ".g_loads", ph + ".g_reduce", ph + ".g_quant", ph + ".g_sync", ph + ".gemv", ph + ".epi", ph + ".bar"]
-names += ["head_ln.epi", "head_ln.bar", "head.g_loads", "head.g_reduce", "head.g_quant", "head.g_sync", "head.gemv"]
+# stamp layout (token_kernel.cuh): start | ln0+stats, publish | per layer 21 | head 4 | end
+names = ["ln0.stats", "ln0.pub"]
+layer = ["kvr.wait", "kvr.quant", "kvr.gemv", "kvr.epi",
+         "out.wait", "out.quant", "out.gemv", "out.resid", "out.stats", "out.ln2pub",
+         "rk.wait", "rk.quant", "rk.gemv", "rk.epi",
+         "v.wait", "v.quant", "v.gemv", "v.resid", "v.stats", "v.ln1pub", "v.end"]
+for _ in range(L):
+    names += layer
+names += ["head.wait", "head.quant", "head.gemv", "head.epi", "done"]
 d = np.diff(tr, axis=1)  # [cta, n-1]
+if d.shape[1] != len(names):
+    print("WARNING: %d segments recorded, %d expected" % (d.shape[1], len(names)))
 agg = {}
 for i, nm in enumerate(names[:d.shape[1]]):
     agg.setdefault(nm, []).append(d[:, i])
-print("%-12s %8s %8s %8s %8s   (us; mean over CTAs and layers, then min/max of per-CTA means)" % ("segment", "mean", "median", "min", "max"))
+print("%-12s %8s %8s %8s %8s   (us; mean over CTAs and layers, median, min/max of per-CTA means)" % ("segment", "mean", "median", "min", "max"))
 tot = 0
+groups = {}
 for nm, lst in agg.items():
     a = np.stack(lst, 1) / 1e3  # [cta, layers]
-    per_layer = a.mean()
     tot += a.mean(0).sum()
-    print("%-12s %8.2f %8.2f %8.2f %8.2f   x%d" % (nm, per_layer, np.median(a), a.mean(1).min(), a.mean(1).max(), a.shape[1]))
-print("sum of means (us):", tot)
-# arrival skew at barriers: spread of the stamp just before each barrier
-bar_idx = [i for i, nm in enumerate(names[:d.shape[1]]) if nm.endswith(".bar")]
-skew = [(tr[:, i].max() - tr[:, i].min()) / 1e3 for i in bar_idx]
-print("arrival skew at barriers (us): mean %.2f median %.2f max %.2f" % (np.mean(skew), np.median(skew), np.max(skew)))
-lat = [(tr[:, i + 1].min() - tr[:, i].max()) / 1e3 for i in bar_idx]
-print("barrier release latency after LAST arrival (us): mean %.2f median %.2f" % (np.mean(lat), np.median(lat)))
+    print("%-12s %8.2f %8.2f %8.2f %8.2f   x%d" % (nm, a.mean(), np.median(a), a.mean(1).min(), a.mean(1).max(), a.shape[1]))
+    kind = nm.split(".")[1]
+    if nm.split(".")[0] in ("kvr", "out", "rk", "v"):
+        groups[kind] = groups.get(kind, 0.0) + a.mean()
+print("sum of means (us):", round(tot, 1))
+print("per layer (us):", {k: round(v, 2) for k, v in groups.items()}, "total", round(sum(groups.values()), 2))
 
 # ---- tile-level: how far ahead of the consumers does the producer run? -------------------------
 tt = eng.read_tile_trace().astype(np.int64)
-n_cta = 148
 for cta in (0, 77):
     issue, ready = tt[0, cta], tt[1, cta]
     n_t = int((issue > 0).sum())
     issue, ready = (issue[:n_t] - t0) / 1e3, (ready[:n_t] - t0) / 1e3
     d_t = np.diff(ready)
-    inside = d_t[d_t < 2.0]  # consecutive tiles of one streaming phase (gaps are phase boundaries)
+    inside = d_t[d_t < 1.2]  # consecutive tiles of one streaming phase (gaps are phase boundaries)
     print("CTA %d: tiles %d; tile period inside a phase (us): median %.3f mean %.3f p90 %.3f" % (
         cta, n_t, np.median(inside), inside.mean(), np.percentile(inside, 90)))
-    per_layer = 48 if workload == "7b" else None
-    if per_layer:
-        base = 2 * per_layer
-        print("layer-2 tiles of CTA %d: idx issue(us) started(us) lead(us)" % cta)
-        for i in range(base, min(base + per_layer, n_t)):
-            print("%4d %9.2f %9.2f %7.2f" % (i - base, issue[i], ready[i], ready[i] - issue[i]))
-print("layer-2 stamps (CTA 0, us):", np.round(tr[0, 3 + 2 * 32:3 + 3 * 32] / 1e3, 2))
+    lead = ready - issue
+    print("CTA %d: lead of the producer (issue -> consumed), us: median %.2f p10 %.2f p90 %.2f" % (
+        cta, np.median(lead), np.percentile(lead, 10), np.percentile(lead, 90)))
+lay = 3 + 21 * min(2, L - 1)
+print("layer-2 stamps (CTA 0, us):", np.round(tr[0, lay:lay + 22] / 1e3, 2))
+eng.close()

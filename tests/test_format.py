@@ -56,6 +56,6 @@ def test_abi_header_symbols_exported(pkg):
     missing = [n for n in names if not hasattr(lib, n)]
     assert not missing, missing
     lib2 = pkg.load_library()
-    assert lib2.rwkv_b200_abi_version() == 1
+    assert lib2.rwkv_b200_abi_version() == 2
     nm = subprocess.run(["nm", "-D", "--defined-only", pkg.lib_path()], capture_output=True, text=True).stdout
     assert "oracle" not in nm.lower()  # the product never links the checker
