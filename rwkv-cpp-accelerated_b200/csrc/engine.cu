@@ -203,14 +203,28 @@ int read_exact(int fd, void *dst, size_t n, uint64_t off) {
 // group reads only the columns / rows it streams.
 int upload_rows(M *m, FileReader &fr, uint64_t off, size_t rows, size_t row_stride, size_t col0, size_t cols, void *dst) {
     uint8_t *d = (uint8_t *)dst;
-    const size_t per = std::max<size_t>(1, fr.pin_bytes / cols);
+    if (cols == row_stride) { // whole rows: one contiguous byte range
+        size_t n = rows * cols;
+        while (n) {
+            const size_t c = std::min(n, fr.pin_bytes);
+            int rc = read_exact(fr.fd, fr.pin, c, off);
+            if (rc) return rc;
+            CK(cudaMemcpyAsync(d, fr.pin, c, cudaMemcpyHostToDevice, m->stream));
+            CK(cudaStreamSynchronize(m->stream));
+            d += c;
+            off += c;
+            n -= c;
+        }
+        return 0;
+    }
+    if (cols > fr.pin_bytes) return fail(4, "row slice of %zu bytes exceeds the staging buffer", cols);
+    const size_t per = fr.pin_bytes / cols;
     for (size_t r = 0; r < rows; r += per) {
         const size_t n = std::min(per, rows - r);
-        int rc = 0;
-        if (cols == row_stride) rc = read_exact(fr.fd, fr.pin, n * cols, off + r * row_stride);
-        else
-            for (size_t i = 0; i < n && !rc; ++i) rc = read_exact(fr.fd, fr.pin + i * cols, cols, off + (r + i) * row_stride + col0);
-        if (rc) return rc;
+        for (size_t i = 0; i < n; ++i) {
+            int rc = read_exact(fr.fd, fr.pin + i * cols, cols, off + (r + i) * row_stride + col0);
+            if (rc) return rc;
+        }
         CK(cudaMemcpyAsync(d + r * cols, fr.pin, n * cols, cudaMemcpyHostToDevice, m->stream));
         CK(cudaStreamSynchronize(m->stream));
     }
