@@ -73,6 +73,8 @@ struct Params {
     int feed_mode;          // 0: ctrl->token, 1: ctrl->next (free-running), 2: stream[ctrl->pos]
     int greedy;             // 1: finish with an on-device argmax into ctrl->next
     int issue_gap;          // minimum SM cycles between two bulk-copy issues of the producer (0 = unpaced)
+    int window;             // bulk copies in flight per CTA (<= stages)
+    int poll_first;         // gather: 1 = poll the first 16 bytes before fetching the rest, 0 = fetch everything at once
     unsigned int ep0;       // epoch before this token: layer l tags its exchanges with ep0 + 1 + l
     unsigned int tk;        // token epoch (tags of the once-per-token exchanges)
     unsigned int timeout_ms;
@@ -99,8 +101,8 @@ struct Params {
     // The exchange block of this rank (one allocation, peer-mapped by the other ranks). Offsets are the
     // same on every rank: xch[g] + off is rank g's copy as seen from here (xch[rank] = the local one).
     unsigned char *xch[kMaxRanks];
-    unsigned int off_stat[2];   // [grid] StatRec  (LN1 / LN_out, LN2)
-    unsigned int off_off[5];    // [grid] OffRec   (kvr, out, rk, v, head)
+    unsigned int off_stat[2];   // [2][grid] tagged doubles: slice sums, slice M2 (LN1 / LN_out, LN2)
+    unsigned int off_off[5];    // [3][grid] tagged doubles: partial offset sums per vector (kvr, out, rk, v, head)
     unsigned int off_vec[5];    // f32+tag vectors (kvr 3E, out Er, rk 2E, v 4Er, head E)
     unsigned int off_in[2];     // [G][E] tagged doubles: partial sums from every rank (out-proj, ffn-V)
     unsigned int off_sr;        // [E] tagged f32: sigmoid(ffn r) of every channel

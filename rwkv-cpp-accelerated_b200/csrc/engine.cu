@@ -327,6 +327,8 @@ int do_load(M *m, const char *path, int quiet) {
     p.plane_cap = (int)(12 * E);
     p.timeout_ms = G > 1 ? 60000u : 4000u;
     configure_ring(m);
+    p.window = std::min(p.stages, 2);
+    p.poll_first = 1;
     if (p.stages < 2) return fail(5, "n_embed=%llu leaves no room for a two-stage ring", E);
     if (!grid_fits(E, Er, Vr, m->grid)) return fail(5, "a grid of %d CTAs does not fit n_embed=%llu", m->grid, E);
     const bool full = E == (unsigned long long)m->cpl * 512ull;
@@ -416,8 +418,8 @@ int do_load(M *m, const char *path, int quiet) {
             return o;
         };
         const size_t nb = (size_t)m->grid;
-        for (int i = 0; i < 2; ++i) p.off_stat[i] = (unsigned int)take(nb * sizeof(rk::StatRec));
-        for (int i = 0; i < 5; ++i) p.off_off[i] = (unsigned int)take(nb * sizeof(rk::OffRec));
+        for (int i = 0; i < 2; ++i) p.off_stat[i] = (unsigned int)take(2 * nb * sizeof(rk::TaggedDouble));
+        for (int i = 0; i < 5; ++i) p.off_off[i] = (unsigned int)take(3 * nb * sizeof(rk::TaggedDouble));
         const size_t vlen[5] = {3 * E, Er, 2 * E, 4 * Er, E};
         for (int i = 0; i < 5; ++i) p.off_vec[i] = (unsigned int)take(vlen[i] * 4);
         for (int i = 0; i < 2; ++i) p.off_in[i] = (unsigned int)take(G * E * sizeof(rk::TaggedDouble));
@@ -778,6 +780,11 @@ int rwkv_b200_set_option(rwkv_b200_model *m, const char *key, const char *value)
     else if (k == "issue_gap") {
         if (v < 0 || v > 100000) return fail(1, "issue_gap is a cycle count in 0..100000");
         m->p.issue_gap = v;
+    } else if (k == "window") {
+        if (v < 1 || v > rk::kMaxStages) return fail(1, "window must be 1..%d", rk::kMaxStages);
+        m->p.window = v;
+    } else if (k == "poll_first") {
+        m->p.poll_first = v != 0;
     } else if (k == "timeout_ms") {
         if (v < 1) return fail(1, "timeout_ms must be positive");
         m->p.timeout_ms = (unsigned int)v;

@@ -23,9 +23,7 @@
 
 namespace rk {
 
-struct __align__(32) StatRec { unsigned long long w[4]; };  // {sum lo, sum hi, M2 lo, M2 hi}, tagged
-struct __align__(64) OffRec { unsigned long long w[8]; };   // up to three tagged doubles (+ padding)
-struct __align__(16) TaggedDouble { unsigned long long w[2]; };
+struct __align__(16) TaggedDouble { unsigned long long w[2]; }; // {lo32 | tag, hi32 | tag}
 
 __device__ __forceinline__ unsigned long long tag64(uint32_t payload, uint32_t tag) {
     return ((unsigned long long)tag << 32) | (unsigned long long)payload;

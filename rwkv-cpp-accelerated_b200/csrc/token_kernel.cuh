@@ -68,11 +68,19 @@ __host__ __device__ inline Slices make_slices(int E, int Er, int Vr, int b, int 
 // Weights are row-major [out][in] int8. A tile is exactly eight work units; a unit is one row segment
 // (rows of <= E bytes: one unit per row, eight rows per tile; ffn-V rows of 4*Er bytes: four units per
 // row, two rows per tile), so consumer warp w always takes unit w of every tile.
+// `window`: at most that many bulk copies of this CTA are in flight (issued, not landed). The memory
+// system serves the SMs' copies in order, so everything in flight queues AHEAD of the small latency-
+// critical loads of an exchange: 5 x 32 KB per SM is 3.7 us of queue at the HBM rate, two tiles are
+// enough to keep HBM saturated. The ring still holds `stages` landed tiles.
 __device__ __forceinline__ void produce_sub(const Params &p, uint32_t ring, uint32_t full0, uint32_t empty0,
-                                            const int8_t *base, int N, int tr, int r0, int nr, RingPos &rp,
+                                            const int8_t *base, int N, int tr, int r0, int nr, RingPos &rp, RingPos &wp,
                                             uint64_t policy, int &tcount, unsigned long long *ptrace, long long &last_issue) {
     for (int r = 0; r < nr; r += tr) {
         const uint32_t bytes = (uint32_t)(min(tr, nr - r) * N);
+        if (tcount >= p.window) { // tile (tcount - window) must have landed
+            mbar_wait(p, full0 + 8 * wp.stage, wp.phase, kDiagRingFull);
+            wp.advance((uint32_t)p.stages);
+        }
         // first pass over the ring: a fresh mbarrier reports the "previous" phase as complete
         mbar_wait(p, empty0 + 8 * rp.stage, rp.phase ^ 1, kDiagRingEmpty);
         if (p.issue_gap > 0) {
@@ -97,20 +105,20 @@ __device__ __forceinline__ void produce_token(const Params &p, const Smem &sm, c
     const uint64_t pol = policy_evict_first();
     const int E = p.E, Er = p.Er;
     const uint32_t ring = smem_u32(sm.ring), full0 = smem_u32(sm.full), empty0 = smem_u32(sm.empty);
-    RingPos rp{0, 0};
+    RingPos rp{0, 0}, wp{0, 0};
     int tcount = 0;
     long long last_issue = 0;
     for (int l = 0; l < p.L_run; ++l) {
         const size_t mc = (size_t)l * Er * E; // column-split matrices [Er][E]
-        produce_sub(p, ring, full0, empty0, p.wk + mc, E, 8, sl.c0, sl.nc, rp, pol, tcount, ptrace, last_issue);
-        produce_sub(p, ring, full0, empty0, p.wv + mc, E, 8, sl.c0, sl.nc, rp, pol, tcount, ptrace, last_issue);
-        produce_sub(p, ring, full0, empty0, p.wr + mc, E, 8, sl.c0, sl.nc, rp, pol, tcount, ptrace, last_issue);
-        produce_sub(p, ring, full0, empty0, p.wo + mc, Er, 8, sl.e0, sl.ne, rp, pol, tcount, ptrace, last_issue);
-        produce_sub(p, ring, full0, empty0, p.wfr + mc, E, 8, sl.c0, sl.nc, rp, pol, tcount, ptrace, last_issue);
-        produce_sub(p, ring, full0, empty0, p.wfk + 4 * mc, E, 8, sl.k0, sl.nk, rp, pol, tcount, ptrace, last_issue);
-        produce_sub(p, ring, full0, empty0, p.wfv + 4 * mc, 4 * Er, 2, sl.e0, sl.ne, rp, pol, tcount, ptrace, last_issue);
+        produce_sub(p, ring, full0, empty0, p.wk + mc, E, 8, sl.c0, sl.nc, rp, wp, pol, tcount, ptrace, last_issue);
+        produce_sub(p, ring, full0, empty0, p.wv + mc, E, 8, sl.c0, sl.nc, rp, wp, pol, tcount, ptrace, last_issue);
+        produce_sub(p, ring, full0, empty0, p.wr + mc, E, 8, sl.c0, sl.nc, rp, wp, pol, tcount, ptrace, last_issue);
+        produce_sub(p, ring, full0, empty0, p.wo + mc, Er, 8, sl.e0, sl.ne, rp, wp, pol, tcount, ptrace, last_issue);
+        produce_sub(p, ring, full0, empty0, p.wfr + mc, E, 8, sl.c0, sl.nc, rp, wp, pol, tcount, ptrace, last_issue);
+        produce_sub(p, ring, full0, empty0, p.wfk + 4 * mc, E, 8, sl.k0, sl.nk, rp, wp, pol, tcount, ptrace, last_issue);
+        produce_sub(p, ring, full0, empty0, p.wfv + 4 * mc, 4 * Er, 2, sl.e0, sl.ne, rp, wp, pol, tcount, ptrace, last_issue);
     }
-    produce_sub(p, ring, full0, empty0, p.whead, E, 8, sl.v0, sl.nv, rp, pol, tcount, ptrace, last_issue);
+    produce_sub(p, ring, full0, empty0, p.whead, E, 8, sl.v0, sl.nv, rp, wp, pol, tcount, ptrace, last_issue);
 }
 
 // ---- consumer core -----------------------------------------------------------------------------------
@@ -251,7 +259,7 @@ __device__ __forceinline__ void trace_stamp(unsigned long long *trace, double *s
 // Inlined ONCE (the phase loop of the kernel has a single call site): as a separate function it would be
 // compiled against the 168-register launch budget instead of the consumers' 232 and spill.
 constexpr int kGatherMax = 20; // 16-byte groups per thread: 256 x 20 x 4 >= 4 * 5120
-__device__ __forceinline__ void gather(const Params &p, const Smem &sm, const float *vec, const OffRec *offrec, int nvec,
+__device__ __forceinline__ void gather(const Params &p, const Smem &sm, const float *vec, const TaggedDouble *offrec, int nvec,
                                        int N, uint32_t tag, unsigned int layer, int ctid, unsigned long long *trace) {
     const uint32_t tag2 = tag & 3u;
     const int ng = N >> 2;        // groups per vector
@@ -268,7 +276,8 @@ __device__ __forceinline__ void gather(const Params &p, const Smem &sm, const fl
     uint4 f[kGatherMax];
     Waiter wt = waiter_begin();
     f[0] = absent;
-    if (cnt > 0) {
+    if (cnt > 0 && p.poll_first == 0) f[0] = ld_vec4(src + index(0));
+    if (cnt > 0 && p.poll_first != 0) {
         const uint4 *s0 = src + index(0);
         f[0] = ld_vec4(s0);
         while (!vec4_ok(f[0], tag2)) {
@@ -281,44 +290,56 @@ __device__ __forceinline__ void gather(const Params &p, const Smem &sm, const fl
         f[i] = absent;
         if (i < cnt) f[i] = ld_vec4(src + index(i));
     }
-    // partial offset sums of the owners (warp 7): record r, r+32, ... in ascending order, then a fixed tree
+    // partial offset sums of the owners (warp 7): all records in flight at once (lane r, r+32, ...), re-read
+    // what has not arrived, then add in ascending order and a fixed tree
     if ((ctid >> 5) == kWarps - 1) {
         const int lane = ctid & 31;
-        double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-        for (int r = lane; r < (int)gridDim.x; r += 32) {
-            unsigned long long a0, a1, a2 = 0, a3 = 0, a4 = 0, a5 = 0;
-            for (;;) {
-                ld_pair(&offrec[r].w[0], a0, a1, false);
-                bool ok = tags_ok(a0, a1, tag);
-                if (nvec > 1) {
-                    ld_pair(&offrec[r].w[2], a2, a3, false);
-                    ok = ok && tags_ok(a2, a3, tag);
-                }
-                if (nvec > 2) {
-                    ld_pair(&offrec[r].w[4], a4, a5, false);
-                    ok = ok && tags_ok(a4, a5, tag);
-                }
-                if (ok) break;
-                if (waiter_tick(p, wt)) wait_expired(p, kDiagOff, layer, (unsigned int)nvec, tag, (unsigned int)(a0 >> 32), (unsigned long long)r);
+        constexpr int kPer = (kMaxGrid + 31) / 32;
+        const unsigned long long none = tag64(0u, tag);
+        unsigned long long a[3][kPer], b[3][kPer];
+#pragma unroll
+        for (int v = 0; v < 3; ++v) {
+#pragma unroll
+            for (int i = 0; i < kPer; ++i) {
+                a[v][i] = none;
+                b[v][i] = none;
+                if (v < nvec && lane + 32 * i < (int)gridDim.x) ld_pair(&offrec[v * (int)gridDim.x + lane + 32 * i], a[v][i], b[v][i], false);
             }
-            s0 += pair_to_double(a0, a1);
-            if (nvec > 1) s1 += pair_to_double(a2, a3);
-            if (nvec > 2) s2 += pair_to_double(a4, a5);
         }
-        s0 = warp_sum(s0);
-        s1 = warp_sum(s1);
-        s2 = warp_sum(s2);
+        for (;;) {
+            bool bad = false;
+#pragma unroll
+            for (int v = 0; v < 3; ++v) {
+#pragma unroll
+                for (int i = 0; i < kPer; ++i) {
+                    if (!tags_ok(a[v][i], b[v][i], tag)) {
+                        ld_pair(&offrec[v * (int)gridDim.x + lane + 32 * i], a[v][i], b[v][i], false);
+                        bad = true;
+                    }
+                }
+            }
+            if (!bad) break;
+            if (waiter_tick(p, wt)) wait_expired(p, kDiagOff, layer, (unsigned int)nvec, tag, (unsigned int)(a[0][0] >> 32), (unsigned long long)lane);
+        }
+        double sv[3];
+#pragma unroll
+        for (int v = 0; v < 3; ++v) {
+            double t = 0.0;
+#pragma unroll
+            for (int i = 0; i < kPer; ++i) t += pair_to_double(a[v][i], b[v][i]);
+            sv[v] = warp_sum(t);
+        }
         if (lane == 0) {
-            sm.scal[3] = s0;
-            sm.scal[4] = s1;
-            sm.scal[5] = s2;
+            sm.scal[3] = sv[0];
+            sm.scal[4] = sv[1];
+            sm.scal[5] = sv[2];
         }
     }
     // late words: re-read until every group carries the tag
     for (;;) {
         bool bad = false;
 #pragma unroll
-        for (int i = 1; i < kGatherMax; ++i) {
+        for (int i = 0; i < kGatherMax; ++i) {
             if (!vec4_ok(f[i], tag2)) {
                 f[i] = ld_vec4(src + index(i));
                 bad = true;
@@ -377,45 +398,54 @@ __device__ __forceinline__ void gather(const Params &p, const Smem &sm, const fl
 // c = the reference's f32-rounded mean this is exactly its second pass (rwkv.cu:432-450), and the two
 // accumulators are rounded to f32 like its float atomics (412-465, 43-44). Called by warps 0 and 1
 // (the slice owners); xown holds the slice. Returns mean and sqrt(var) (unbiased, no epsilon).
-__device__ __noinline__ void slice_stats(const Params &p, const Smem &sm, StatRec *recs, int ne, uint32_t tag,
+__device__ __noinline__ void slice_stats(const Params &p, const Smem &sm, TaggedDouble *recs, int ne, uint32_t tag,
                                          unsigned int layer, int ctid, double &xmean, double &x2) {
     own_sync(); // xown complete
     if (ctid < 32) {
         const int lane = ctid;
+        const int nb = (int)gridDim.x;
+        TaggedDouble *const sums = recs, *const m2s = recs + nb; // [nb] each
         const double v0 = lane < ne ? sm.xown[lane] : 0.0, v1 = lane + 32 < ne ? sm.xown[lane + 32] : 0.0;
         const double s = warp_sum(v0 + v1);
         const double mb = s / (double)ne;
         const double d0 = lane < ne ? v0 - mb : 0.0, d1 = lane + 32 < ne ? v1 - mb : 0.0;
         const double m2 = warp_sum(d0 * d0 + d1 * d1);
         if (lane == 0) {
-            const unsigned long long us = (unsigned long long)__double_as_longlong(s), um = (unsigned long long)__double_as_longlong(m2);
-            StatRec *mine = recs + blockIdx.x;
-            st_pair(&mine->w[0], tag64((uint32_t)us, tag), tag64((uint32_t)(us >> 32), tag), false);
-            st_pair(&mine->w[2], tag64((uint32_t)um, tag), tag64((uint32_t)(um >> 32), tag), false);
+            st_tagged_double(&sums[blockIdx.x], s, tag, false);
+            st_tagged_double(&m2s[blockIdx.x], m2, tag, false);
         }
-        // every CTA's record: r = lane, lane+32, ... ascending, then fixed trees
+        // every CTA's record: all in flight at once (r = lane, lane+32, ...), re-read what has not arrived
         constexpr int kPer = (kMaxGrid + 31) / 32;
-        double sb[kPer], mb2[kPer];
-        double stot = 0.0;
-        Waiter w = waiter_begin();
+        const unsigned long long none = tag64(0u, tag);
+        unsigned long long a[kPer], b[kPer], c[kPer], d[kPer];
 #pragma unroll
         for (int i = 0; i < kPer; ++i) {
-            const int r = lane + 32 * i;
-            sb[i] = 0.0;
-            mb2[i] = 0.0;
-            if (r < (int)gridDim.x) {
-                unsigned long long a, b, c, d;
-                for (;;) {
-                    ld_pair(&recs[r].w[0], a, b, false);
-                    ld_pair(&recs[r].w[2], c, d, false);
-                    if (tags_ok(a, b, tag) && tags_ok(c, d, tag)) break;
-                    if (waiter_tick(p, w)) wait_expired(p, kDiagStats, layer, 0, tag, (unsigned int)(a >> 32), (unsigned long long)r);
-                }
-                sb[i] = pair_to_double(a, b);
-                mb2[i] = pair_to_double(c, d);
-                stot += sb[i];
+            a[i] = b[i] = c[i] = d[i] = none;
+            if (lane + 32 * i < nb) {
+                ld_pair(&sums[lane + 32 * i], a[i], b[i], false);
+                ld_pair(&m2s[lane + 32 * i], c[i], d[i], false);
             }
         }
+        Waiter w = waiter_begin();
+        for (;;) {
+            bool bad = false;
+#pragma unroll
+            for (int i = 0; i < kPer; ++i) {
+                if (!tags_ok(a[i], b[i], tag)) {
+                    ld_pair(&sums[lane + 32 * i], a[i], b[i], false);
+                    bad = true;
+                }
+                if (!tags_ok(c[i], d[i], tag)) {
+                    ld_pair(&m2s[lane + 32 * i], c[i], d[i], false);
+                    bad = true;
+                }
+            }
+            if (!bad) break;
+            if (waiter_tick(p, w)) wait_expired(p, kDiagStats, layer, 0, tag, (unsigned int)(a[0] >> 32), (unsigned long long)lane);
+        }
+        double stot = 0.0;
+#pragma unroll
+        for (int i = 0; i < kPer; ++i) stot += pair_to_double(a[i], b[i]);
         stot = warp_sum(stot);
         const float mean_acc = (float)stot;
         const double mean_f = (double)(mean_acc / (float)p.E);
@@ -423,11 +453,11 @@ __device__ __noinline__ void slice_stats(const Params &p, const Smem &sm, StatRe
 #pragma unroll
         for (int i = 0; i < kPer; ++i) {
             const int r = lane + 32 * i;
-            if (r < (int)gridDim.x) {
+            if (r < nb) {
                 int r0, n;
-                split_rows(p.E, r, (int)gridDim.x, r0, n);
-                const double dm = sb[i] / (double)n - mean_f;
-                q += mb2[i] + (double)n * dm * dm;
+                split_rows(p.E, r, nb, r0, n);
+                const double dm = pair_to_double(a[i], b[i]) / (double)n - mean_f;
+                q += pair_to_double(c[i], d[i]) + (double)n * dm * dm;
             }
         }
         q = warp_sum(q);
@@ -445,7 +475,7 @@ __device__ __noinline__ void slice_stats(const Params &p, const Smem &sm, StatRe
 // OffRec. Fixed reduction shape: shuffle tree per warp, then warps 0..nw-1 in order. Called by every
 // consumer warp; warps without data return at once. (NV > 1 only for slice owners: <= 2 warps.)
 template <int NV>
-__device__ __forceinline__ void publish_offsums(const Smem &sm, OffRec *recs, double (&of)[NV], uint32_t tag, int ctid, int nact) {
+__device__ __forceinline__ void publish_offsums(const Smem &sm, TaggedDouble *recs, double (&of)[NV], uint32_t tag, int ctid, int nact) {
     const int nw = nact > 0 ? (nact + 31) >> 5 : 1; // an empty slice still publishes zeros
     const int w = ctid >> 5;
     if (w >= nw) return;
@@ -466,9 +496,8 @@ __device__ __forceinline__ void publish_offsums(const Smem &sm, OffRec *recs, do
         }
     }
     if (ctid == 0) {
-        OffRec *mine = recs + blockIdx.x;
 #pragma unroll
-        for (int k = 0; k < NV; ++k) st_tagged_double(&mine->w[2 * k], of[k], tag, false);
+        for (int k = 0; k < NV; ++k) st_tagged_double(&recs[k * (int)gridDim.x + blockIdx.x], of[k], tag, false); // [NV][grid]
     }
 }
 
@@ -555,8 +584,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_token(const __grid_constant__ P
     else if (p.feed_mode == 2) token = p.stream[ctrl->pos];
     const size_t so = (size_t)ctrl->slot * p.L * E; // state slot offset
     unsigned char *const xl = p.xch[p.rank];
-    StatRec *const stat0 = reinterpret_cast<StatRec *>(xl + p.off_stat[0]);
-    StatRec *const stat1 = reinterpret_cast<StatRec *>(xl + p.off_stat[1]);
+    TaggedDouble *const stat0 = reinterpret_cast<TaggedDouble *>(xl + p.off_stat[0]);
+    TaggedDouble *const stat1 = reinterpret_cast<TaggedDouble *>(xl + p.off_stat[1]);
     const double *const saa = reinterpret_cast<const double *>(xl + p.off_saa);
     const double *const sbb = reinterpret_cast<const double *>(xl + p.off_sbb);
     double *const pd = sm.pd + (ctid & (kMaxSlice - 1)) * 8; // this owner thread's parameter slots
@@ -665,7 +694,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_token(const __grid_constant__ P
                 of[2] = (double)fr * (double)pf[5];
                 p.sxy[so + (size_t)l * E + j] = ln; // only the owner ever reads or writes this element
             }
-            publish_offsums<3>(sm, reinterpret_cast<OffRec *>(xl + p.off_off[0]), of, ep, ctid, ne);
+            publish_offsums<3>(sm, reinterpret_cast<TaggedDouble *>(xl + p.off_off[0]), of, ep, ctid, ne);
         } else {
             float *const vec_h = reinterpret_cast<float *>(xl + p.off_vec[4]);
             double of[1] = {0};
@@ -676,7 +705,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_token(const __grid_constant__ P
                 of[0] = (double)f * (double)pf[1];
                 p.x[j] = sm.xown[ctid]; // residual stream after the last layer (debug / tests)
             }
-            publish_offsums<1>(sm, reinterpret_cast<OffRec *>(xl + p.off_off[4]), of, p.tk, ctid, ne);
+            publish_offsums<1>(sm, reinterpret_cast<TaggedDouble *>(xl + p.off_off[4]), of, p.tk, ctid, ne);
         }
         stamp();
     };
@@ -705,7 +734,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_token(const __grid_constant__ P
         default: nvec = 1; N = E; nseg = 1; nsub = 1; nr0 = sl.nv; nr1 = 0; tag = p.tk; break;      // head
         }
         const float *vec = reinterpret_cast<const float *>(xl + p.off_vec[ph]);
-        const OffRec *offrec = reinterpret_cast<const OffRec *>(xl + p.off_off[ph]);
+        const TaggedDouble *offrec = reinterpret_cast<const TaggedDouble *>(xl + p.off_off[ph]);
         // -------- park the epilogue's parameters in shared memory ------------------------------------
         if (ph == 0) {
             if (owner_warps) { // WKV of channel cg (clamped: an idle thread reads a valid address)
@@ -781,7 +810,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_token(const __grid_constant__ P
                     st_f32(reinterpret_cast<float *>(xl + p.off_vec[1]) + cl, tag_f32(xo, ep & 3u));
                     of[0] = (double)rw * (double)pf[1];
                 }
-                publish_offsums<1>(sm, reinterpret_cast<OffRec *>(xl + p.off_off[1]), of, ep, ctid, nc);
+                publish_offsums<1>(sm, reinterpret_cast<TaggedDouble *>(xl + p.off_off[1]), of, ep, ctid, nc);
             }
         } else if (ph == 1) {
             // ======== residual (rwkv.cu:548-553), then LN2 + token shift (557-562) ========================
@@ -812,7 +841,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_token(const __grid_constant__ P
                     of[1] = (double)fk * (double)pf[3];
                     p.sdd[so + lo + j] = ln;
                 }
-                publish_offsums<2>(sm, reinterpret_cast<OffRec *>(xl + p.off_off[2]), of, ep, ctid, ne);
+                publish_offsums<2>(sm, reinterpret_cast<TaggedDouble *>(xl + p.off_off[2]), of, ep, ctid, ne);
             }
         } else if (ph == 2) {
             // ======== sigmoid(ffn r) for the own channels, relu^2 of the own key channels (566-573) =======
@@ -832,7 +861,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_token(const __grid_constant__ P
                 st_f32(reinterpret_cast<float *>(xl + p.off_vec[3]) + sl.k0 + ctid, tag_f32(xv, ep & 3u));
                 of[0] = (double)a * (double)pk[1];
             }
-            publish_offsums<1>(sm, reinterpret_cast<OffRec *>(xl + p.off_off[3]), of, ep, ctid, nk);
+            publish_offsums<1>(sm, reinterpret_cast<TaggedDouble *>(xl + p.off_off[3]), of, ep, ctid, nk);
         } else if (ph == 3) {
             // ======== residual (rwkv.cu:574-577), then the next layer's LN1 (or LN_out) ====================
             if (owner_warps) {

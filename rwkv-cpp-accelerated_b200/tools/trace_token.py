@@ -16,6 +16,9 @@ ntok = int(sys.argv[2]) if len(sys.argv) > 2 else 4
 L, E = bench.SHAPES[workload]
 eng = pkg.Engine(bench.model_path(workload, pkg))
 eng.set_option("trace", 1)
+for kv in sys.argv[3:]:
+    k, v = kv.split("=")
+    eng.set_option(k, v)
 tok = bench.SEED_TOKEN
 for _ in range(ntok):
     tok = eng.forward_greedy(tok)
@@ -47,7 +50,7 @@ for nm, lst in agg.items():
     a = np.stack(lst, 1) / 1e3  # [cta, layers]
     tot += a.mean(0).sum()
     print("%-12s %8.2f %8.2f %8.2f %8.2f   x%d" % (nm, a.mean(), np.median(a), a.mean(1).min(), a.mean(1).max(), a.shape[1]))
-    kind = nm.split(".")[1]
+    kind = nm.split(".")[-1]
     if nm.split(".")[0] in ("kvr", "out", "rk", "v"):
         groups[kind] = groups.get(kind, 0.0) + a.mean()
 print("sum of means (us):", round(tot, 1))
