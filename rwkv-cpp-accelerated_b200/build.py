@@ -71,6 +71,8 @@ def build_oracle(force=False):
     if os.path.exists("/root/reference/include/rwkv/cuda/rwkv.cu"):
         if force or _newer(REF_HARNESS, [os.path.join(ORACLE_DIR, "ref_harness.cpp")]):
             _run(["make", "-C", ORACLE_DIR, "ref"])
+        # the reference's own header / example program on top of this engine (make decides what is stale)
+        _run(["make", "-C", ORACLE_DIR, "ref-b200"])
     return ORACLE_LIB
 
 
