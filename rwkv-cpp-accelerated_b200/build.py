@@ -53,7 +53,9 @@ def build_engine(force=False):
     srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))]
     srcs.append(os.path.join(ROOT, "include", "rwkv_b200.h"))
     if force or _newer(LIB, srcs):
-        _run([nvcc()] + NVCC_FLAGS + ["-o", LIB, os.path.join(CSRC, "engine.cu")])
+        tmp = LIB + ".tmp%d" % os.getpid()  # a snapshot taken during the build never sees a half-written library
+        _run([nvcc()] + NVCC_FLAGS + ["-o", tmp, os.path.join(CSRC, "engine.cu")])
+        os.replace(tmp, LIB)
     return LIB
 
 

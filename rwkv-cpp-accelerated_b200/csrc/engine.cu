@@ -328,7 +328,7 @@ int do_load(M *m, const char *path, int quiet) {
     p.timeout_ms = G > 1 ? 60000u : 4000u;
     configure_ring(m);
     p.window = std::min(p.stages, 2);
-    p.poll_first = 1;
+    p.poll_first = 2;
     if (p.stages < 2) return fail(5, "n_embed=%llu leaves no room for a two-stage ring", E);
     if (!grid_fits(E, Er, Vr, m->grid)) return fail(5, "a grid of %d CTAs does not fit n_embed=%llu", m->grid, E);
     const bool full = E == (unsigned long long)m->cpl * 512ull;
@@ -784,7 +784,8 @@ int rwkv_b200_set_option(rwkv_b200_model *m, const char *key, const char *value)
         if (v < 1 || v > rk::kMaxStages) return fail(1, "window must be 1..%d", rk::kMaxStages);
         m->p.window = v;
     } else if (k == "poll_first") {
-        m->p.poll_first = v != 0;
+        if (v < 0 || v > 2) return fail(1, "poll_first is 0, 1 or 2");
+        m->p.poll_first = v;
     } else if (k == "timeout_ms") {
         if (v < 1) return fail(1, "timeout_ms must be positive");
         m->p.timeout_ms = (unsigned int)v;

@@ -276,8 +276,12 @@ __device__ __forceinline__ void gather(const Params &p, const Smem &sm, const fl
     uint4 f[kGatherMax];
     Waiter wt = waiter_begin();
     f[0] = absent;
-    if (cnt > 0 && p.poll_first == 0) f[0] = ld_vec4(src + index(0));
-    if (cnt > 0 && p.poll_first != 0) {
+    // poll_first 2: meet at the block barrier first - the owners of THIS CTA have published by then, and the
+    // CTAs run in step, so one batch of loads normally finds everything (one L2 round trip, no polling
+    // traffic while the owners still compute); 1: poll the first 16 bytes, then the batch; 0: batch at once.
+    if (p.poll_first == 2) tok_sync();
+    if (cnt > 0 && p.poll_first != 1) f[0] = ld_vec4(src + index(0));
+    if (cnt > 0 && p.poll_first == 1) {
         const uint4 *s0 = src + index(0);
         f[0] = ld_vec4(s0);
         while (!vec4_ok(f[0], tag2)) {
