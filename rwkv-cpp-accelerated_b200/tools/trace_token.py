@@ -27,6 +27,9 @@ n = int((tr[0] > 0).sum())
 tr = tr[:, :n]
 t0 = tr[:, 0].min()
 tr = tr - t0
+out_dir = os.path.join(ROOT, "gpurun_out")
+if os.path.isdir(out_dir):
+    np.save(os.path.join(out_dir, "trace_raw_%s.npy" % workload), tr.astype(np.int32))
 print("stamps per CTA", n, "token time us", (tr[:, -1].max()) / 1e3)
 # stamp layout (token_kernel.cuh): start | ln0+stats, publish | per layer 21 | head 4 | end
 names = ["ln0.stats", "ln0.pub"]
