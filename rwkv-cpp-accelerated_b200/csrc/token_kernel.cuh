@@ -379,9 +379,9 @@ __device__ __forceinline__ void gather(const Params &p, const Smem &sm, const fl
         uint32_t m = 0u;
 #pragma unroll
         for (int w = 0; w < kWarps; ++w) m = max(m, sm.wmax[w * 4 + v]);
-        const double mm = (double)__uint_as_float(m);
-        inv[v] = mm > 0.0 ? (float)((double)kQMax / mm) : 0.0f;
-        if (ctid == v) sm.scal[v] = mm / (double)kQMax;
+        const float mf = __uint_as_float(m);
+        inv[v] = mf > 0.0f ? (float)kQMax / mf : 0.0f; // IEEE division: the same bits in every CTA
+        if (ctid == v) sm.scal[v] = (double)mf * (1.0 / (double)kQMax);
     }
 #pragma unroll
     for (int i = 0; i < kGatherMax; ++i) {
@@ -397,26 +397,33 @@ __device__ __forceinline__ void gather(const Params &p, const Smem &sm, const fl
 }
 
 // ---- slice statistics -----------------------------------------------------------------------------------
-// Layernorm statistics of the whole residual stream from per-CTA {sum, M2 = sum (x - slice mean)^2},
-// combined without cancellation: sum_j (x_j - c)^2 = sum_b [M2_b + n_b (mean_b - c)^2] for any c. With
-// c = the reference's f32-rounded mean this is exactly its second pass (rwkv.cu:432-450), and the two
-// accumulators are rounded to f32 like its float atomics (412-465, 43-44). Called by warps 0 and 1
-// (the slice owners); xown holds the slice. Returns mean and sqrt(var) (unbiased, no epsilon).
+// Layernorm statistics of the whole residual stream from per-CTA {S = sum x, Q = sum (x - c0)^2} in double,
+// where c0 is a reference point every CTA already knows: the mean of the previous statistics (0 at the
+// start of a token). The residual moves the mean only a little, so Q carries no cancellation, and
+//   sum_j (x_j - c)^2 = Q - 2 (c - c0)(S - E c0) + E (c - c0)^2
+// for the reference's f32-rounded mean c is exactly its second pass (rwkv.cu:432-450); the two accumulators
+// are rounded to f32 like its float atomics (412-465, 43-44). Called by warps 0 and 1 (the slice owners);
+// xown holds the slice. The reader's work after the records arrive is two shuffle reductions and a dozen
+// scalar operations - this sits on the critical path of every layer twice.
+// Returns mean and 1 / sqrt(var) (unbiased, no epsilon); c0 is updated to the new mean.
 __device__ __noinline__ void slice_stats(const Params &p, const Smem &sm, TaggedDouble *recs, int ne, uint32_t tag,
-                                         unsigned int layer, int ctid, double &xmean, double &x2) {
+                                         unsigned int layer, int ctid, double &c0, double &xmean, double &rstd) {
     own_sync(); // xown complete
     if (ctid < 32) {
         const int lane = ctid;
         const int nb = (int)gridDim.x;
-        TaggedDouble *const sums = recs, *const m2s = recs + nb; // [nb] each
+        TaggedDouble *const sums = recs, *const qs = recs + nb; // [nb] each
         const double v0 = lane < ne ? sm.xown[lane] : 0.0, v1 = lane + 32 < ne ? sm.xown[lane + 32] : 0.0;
-        const double s = warp_sum(v0 + v1);
-        const double mb = s / (double)ne;
-        const double d0 = lane < ne ? v0 - mb : 0.0, d1 = lane + 32 < ne ? v1 - mb : 0.0;
-        const double m2 = warp_sum(d0 * d0 + d1 * d1);
+        const double d0 = lane < ne ? v0 - c0 : 0.0, d1 = lane + 32 < ne ? v1 - c0 : 0.0;
+        double s = v0 + v1, q = d0 * d0 + d1 * d1;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { // two independent trees, interleaved
+            s += __shfl_xor_sync(0xffffffffu, s, o);
+            q += __shfl_xor_sync(0xffffffffu, q, o);
+        }
         if (lane == 0) {
             st_tagged_double(&sums[blockIdx.x], s, tag, false);
-            st_tagged_double(&m2s[blockIdx.x], m2, tag, false);
+            st_tagged_double(&qs[blockIdx.x], q, tag, false);
         }
         // every CTA's record: all in flight at once (r = lane, lane+32, ...), re-read what has not arrived
         constexpr int kPer = (kMaxGrid + 31) / 32;
@@ -427,7 +434,7 @@ __device__ __noinline__ void slice_stats(const Params &p, const Smem &sm, Tagged
             a[i] = b[i] = c[i] = d[i] = none;
             if (lane + 32 * i < nb) {
                 ld_pair(&sums[lane + 32 * i], a[i], b[i], false);
-                ld_pair(&m2s[lane + 32 * i], c[i], d[i], false);
+                ld_pair(&qs[lane + 32 * i], c[i], d[i], false);
             }
         }
         Waiter w = waiter_begin();
@@ -440,39 +447,40 @@ __device__ __noinline__ void slice_stats(const Params &p, const Smem &sm, Tagged
                     bad = true;
                 }
                 if (!tags_ok(c[i], d[i], tag)) {
-                    ld_pair(&m2s[lane + 32 * i], c[i], d[i], false);
+                    ld_pair(&qs[lane + 32 * i], c[i], d[i], false);
                     bad = true;
                 }
             }
             if (!bad) break;
             if (waiter_tick(p, w)) wait_expired(p, kDiagStats, layer, 0, tag, (unsigned int)(a[0] >> 32), (unsigned long long)lane);
         }
-        double stot = 0.0;
+        double st = 0.0, qt = 0.0;
 #pragma unroll
-        for (int i = 0; i < kPer; ++i) stot += pair_to_double(a[i], b[i]);
-        stot = warp_sum(stot);
-        const float mean_acc = (float)stot;
-        const double mean_f = (double)(mean_acc / (float)p.E);
-        double q = 0.0;
-#pragma unroll
-        for (int i = 0; i < kPer; ++i) {
-            const int r = lane + 32 * i;
-            if (r < nb) {
-                int r0, n;
-                split_rows(p.E, r, nb, r0, n);
-                const double dm = pair_to_double(a[i], b[i]) / (double)n - mean_f;
-                q += pair_to_double(c[i], d[i]) + (double)n * dm * dm;
-            }
+        for (int i = 0; i < kPer; ++i) { // ascending record index per lane, then fixed trees: deterministic
+            st += pair_to_double(a[i], b[i]);
+            qt += pair_to_double(c[i], d[i]);
         }
-        q = warp_sum(q);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            st += __shfl_xor_sync(0xffffffffu, st, o);
+            qt += __shfl_xor_sync(0xffffffffu, qt, o);
+        }
         if (lane == 0) {
-            sm.scal[6] = (double)mean_acc / (double)p.E;
-            sm.scal[7] = (double)sqrtf((float)q / (float)(p.E - 1));
+            const double Ed = (double)p.E;
+            const float mean_acc = (float)st;
+            const double mean_f = (double)(mean_acc / (float)p.E); // the variance kernel's float / float mean
+            const double dc = mean_f - c0;
+            double m2 = qt - 2.0 * dc * (st - Ed * c0) + Ed * dc * dc;
+            if (m2 < 0.0) m2 = 0.0;
+            const float sd = sqrtf((float)m2 / (float)(p.E - 1));
+            sm.scal[6] = (double)mean_acc / Ed;
+            sm.scal[7] = 1.0 / (double)sd;
         }
     }
     own_sync();
     xmean = sm.scal[6];
-    x2 = sm.scal[7];
+    rstd = sm.scal[7];
+    c0 = xmean;
 }
 
 // Partial offset sums of this CTA (data in the first `nact` consumer threads, NV values each) -> its
@@ -645,6 +653,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_token(const __grid_constant__ P
         tok_sync(); // the scratch in res64 is reused by the first GEMV
     }
 
+    double c0 = 0.0; // reference point of the slice statistics: the previous mean (same value on every CTA)
     // Parameters of the slice computation that follows a residual update, parked in this thread's shared
     // slots: LN1 + att token shift of layer l (l < L_run), or LN_out + head scale (l == L_run).
     auto fetch_ln1 = [&](int l) {
@@ -673,8 +682,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_token(const __grid_constant__ P
     // the last layer, LN_out -> publish the head input (rwkv.cu:585-588). Warps 0 and 1.
     auto slice_to_att = [&](int l) {
         const uint32_t ep = p.ep0 + 1u + (uint32_t)l;
-        double xmean, x2;
-        slice_stats(p, sm, stat0, ne, ep, (unsigned int)l, ctid, xmean, x2);
+        double xmean, rstd;
+        slice_stats(p, sm, stat0, ne, ep, (unsigned int)l, ctid, c0, xmean, rstd);
         stamp();
         cp_async_wait();
         if (l < p.L_run) {
@@ -683,7 +692,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_token(const __grid_constant__ P
             if (mine) {
                 const uint32_t t2 = ep & 3u;
                 const double mk = pd[2], mv = pd[3], mr = pd[4], st = pd[5];
-                const double ln = pd[0] * ((sm.xown[ctid] - xmean) * (1.0 / x2)) + pd[1];
+                const double ln = pd[0] * ((sm.xown[ctid] - xmean) * rstd) + pd[1];
                 const float fk = (float)(mk * ln + (1.0 - mk) * st);
                 const float fv = (float)(mv * ln + (1.0 - mv) * st);
                 const float fr = (float)(mr * ln + (1.0 - mr) * st);
@@ -703,7 +712,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_token(const __grid_constant__ P
             float *const vec_h = reinterpret_cast<float *>(xl + p.off_vec[4]);
             double of[1] = {0};
             if (mine) {
-                const float f = (float)(pd[0] * ((sm.xown[ctid] - xmean) * (1.0 / x2)) + pd[1]);
+                const float f = (float)(pd[0] * ((sm.xown[ctid] - xmean) * rstd) + pd[1]);
                 const float xh = (float)((double)f * (double)pf[0]);
                 st_f32(vec_h + j, tag_f32(xh, p.tk & 3u));
                 of[0] = (double)f * (double)pf[1];
@@ -827,13 +836,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_token(const __grid_constant__ P
                     sm.xown[ctid] = (double)xf;
                 }
                 stamp();
-                double xmean, x2;
-                slice_stats(p, sm, stat1, ne, ep, (unsigned int)l, ctid, xmean, x2);
+                double xmean, rstd;
+                slice_stats(p, sm, stat1, ne, ep, (unsigned int)l, ctid, c0, xmean, rstd);
                 stamp();
                 double of[2] = {0, 0};
                 if (mine) {
                     const double fmk = pd[2], fmr = pd[3], fst = pd[4];
-                    const double ln = pd[0] * ((sm.xown[ctid] - xmean) * (1.0 / x2)) + pd[1];
+                    const double ln = pd[0] * ((sm.xown[ctid] - xmean) * rstd) + pd[1];
                     const float fr = (float)(fmr * ln + (1.0 - fmr) * fst);
                     const float fk = (float)(fmk * ln + (1.0 - fmk) * fst);
                     const float xr = (float)((double)fr * (double)pf[0]);
