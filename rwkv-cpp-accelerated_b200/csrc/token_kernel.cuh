@@ -280,6 +280,7 @@ __device__ __forceinline__ void gather(const Params &p, const Smem &sm, const fl
     // CTAs run in step, so one batch of loads normally finds everything (one L2 round trip, no polling
     // traffic while the owners still compute); 1: poll the first 16 bytes, then the batch; 0: batch at once.
     if (p.poll_first == 2) tok_sync();
+    trace_stamp(trace, sm.scal, ctid); // G1: block met
     if (cnt > 0 && p.poll_first != 1) f[0] = ld_vec4(src + index(0));
     if (cnt > 0 && p.poll_first == 1) {
         const uint4 *s0 = src + index(0);
@@ -372,7 +373,9 @@ __device__ __forceinline__ void gather(const Params &p, const Smem &sm, const fl
         wm[1] = mx1;
         wm[2] = mx2;
     }
+    trace_stamp(trace, sm.scal, ctid); // G3: own maxima written
     tok_sync();
+    trace_stamp(trace, sm.scal, ctid); // G4: all warps (incl. the offset sums of warp 7) done
     float inv[3];
 #pragma unroll
     for (int v = 0; v < 3; ++v) {
@@ -407,8 +410,10 @@ __device__ __forceinline__ void gather(const Params &p, const Smem &sm, const fl
 // scalar operations - this sits on the critical path of every layer twice.
 // Returns mean and 1 / sqrt(var) (unbiased, no epsilon); c0 is updated to the new mean.
 __device__ __noinline__ void slice_stats(const Params &p, const Smem &sm, TaggedDouble *recs, int ne, uint32_t tag,
-                                         unsigned int layer, int ctid, double &c0, double &xmean, double &rstd) {
+                                         unsigned int layer, int ctid, double &c0, double &xmean, double &rstd,
+                                         unsigned long long *trace) {
     own_sync(); // xown complete
+    trace_stamp(trace, sm.scal, ctid); // S1: owners synchronised
     if (ctid < 32) {
         const int lane = ctid;
         const int nb = (int)gridDim.x;
@@ -425,6 +430,7 @@ __device__ __noinline__ void slice_stats(const Params &p, const Smem &sm, Tagged
             st_tagged_double(&sums[blockIdx.x], s, tag, false);
             st_tagged_double(&qs[blockIdx.x], q, tag, false);
         }
+        trace_stamp(trace, sm.scal, ctid); // S2: own record published
         // every CTA's record: all in flight at once (r = lane, lane+32, ...), re-read what has not arrived
         constexpr int kPer = (kMaxGrid + 31) / 32;
         const unsigned long long none = tag64(0u, tag);
@@ -438,6 +444,11 @@ __device__ __noinline__ void slice_stats(const Params &p, const Smem &sm, Tagged
             }
         }
         Waiter w = waiter_begin();
+        if (trace != nullptr && ctid == 0) { // S3: first answers back (forces a wait on the loads)
+            volatile unsigned long long sink = a[0] ^ c[kPer - 1];
+            (void)sink;
+        }
+        trace_stamp(trace, sm.scal, ctid);
         for (;;) {
             bool bad = false;
 #pragma unroll
@@ -454,6 +465,7 @@ __device__ __noinline__ void slice_stats(const Params &p, const Smem &sm, Tagged
             if (!bad) break;
             if (waiter_tick(p, w)) wait_expired(p, kDiagStats, layer, 0, tag, (unsigned int)(a[0] >> 32), (unsigned long long)lane);
         }
+        trace_stamp(trace, sm.scal, ctid); // S4: every record here
         double st = 0.0, qt = 0.0;
 #pragma unroll
         for (int i = 0; i < kPer; ++i) { // ascending record index per lane, then fixed trees: deterministic
@@ -476,6 +488,7 @@ __device__ __noinline__ void slice_stats(const Params &p, const Smem &sm, Tagged
             sm.scal[6] = (double)mean_acc / Ed;
             sm.scal[7] = 1.0 / (double)sd;
         }
+        trace_stamp(trace, sm.scal, ctid); // S5: statistics computed
     }
     own_sync();
     xmean = sm.scal[6];
@@ -683,7 +696,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_token(const __grid_constant__ P
     auto slice_to_att = [&](int l) {
         const uint32_t ep = p.ep0 + 1u + (uint32_t)l;
         double xmean, rstd;
-        slice_stats(p, sm, stat0, ne, ep, (unsigned int)l, ctid, c0, xmean, rstd);
+        slice_stats(p, sm, stat0, ne, ep, (unsigned int)l, ctid, c0, xmean, rstd, c_trace);
         stamp();
         cp_async_wait();
         if (l < p.L_run) {
@@ -837,7 +850,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_token(const __grid_constant__ P
                 }
                 stamp();
                 double xmean, rstd;
-                slice_stats(p, sm, stat1, ne, ep, (unsigned int)l, ctid, c0, xmean, rstd);
+                slice_stats(p, sm, stat1, ne, ep, (unsigned int)l, ctid, c0, xmean, rstd, c_trace);
                 stamp();
                 double of[2] = {0, 0};
                 if (mine) {

@@ -32,14 +32,16 @@ if os.path.isdir(out_dir):
     np.save(os.path.join(out_dir, "trace_raw_%s.npy" % workload), tr.astype(np.int32))
 print("stamps per CTA", n, "token time us", (tr[:, -1].max()) / 1e3)
 # stamp layout (token_kernel.cuh): start | ln0+stats, publish | per layer 21 | head 4 | end
-names = ["ln0.stats", "ln0.pub"]
-layer = ["kvr.wait", "kvr.quant", "kvr.gemv", "kvr.epi",
-         "out.wait", "out.quant", "out.gemv", "out.resid", "out.stats", "out.ln2pub",
-         "rk.wait", "rk.quant", "rk.gemv", "rk.epi",
-         "v.wait", "v.quant", "v.gemv", "v.resid", "v.stats", "v.ln1pub", "v.end"]
+ST = ["st.sync", "st.pub", "st.first", "st.all", "st.calc", "st.ret"]  # slice_stats
+GA = ["g.meet", "g.words", "g.max", "g.sync", "g.quant"]                    # gather
+names = ["ln0." + x for x in ST] + ["ln0.pub"]
+layer = ["kvr." + x for x in GA] + ["kvr.gemv", "kvr.epi"] + \
+        ["out." + x for x in GA] + ["out.gemv", "out.resid"] + ["out." + x for x in ST] + ["out.ln2pub"] + \
+        ["rk." + x for x in GA] + ["rk.gemv", "rk.epi"] + \
+        ["v." + x for x in GA] + ["v.gemv", "v.resid"] + ["v." + x for x in ST] + ["v.ln1pub", "v.end"]
 for _ in range(L):
     names += layer
-names += ["head.wait", "head.quant", "head.gemv", "head.epi", "done"]
+names += ["head." + x for x in GA] + ["head.gemv", "head.epi", "done"]
 d = np.diff(tr, axis=1)  # [cta, n-1]
 if d.shape[1] != len(names):
     print("WARNING: %d segments recorded, %d expected" % (d.shape[1], len(names)))
@@ -53,7 +55,7 @@ for nm, lst in agg.items():
     a = np.stack(lst, 1) / 1e3  # [cta, layers]
     tot += a.mean(0).sum()
     print("%-12s %8.2f %8.2f %8.2f %8.2f   x%d" % (nm, a.mean(), np.median(a), a.mean(1).min(), a.mean(1).max(), a.shape[1]))
-    kind = nm.split(".")[-1]
+    kind = ".".join(nm.split(".")[1:])
     if nm.split(".")[0] in ("kvr", "out", "rk", "v"):
         groups[kind] = groups.get(kind, 0.0) + a.mean()
 print("sum of means (us):", round(tot, 1))
@@ -72,6 +74,5 @@ for cta in (0, 77):
     lead = ready - issue
     print("CTA %d: lead of the producer (issue -> consumed), us: median %.2f p10 %.2f p90 %.2f" % (
         cta, np.median(lead), np.percentile(lead, 10), np.percentile(lead, 90)))
-lay = 3 + 21 * min(2, L - 1)
-print("layer-2 stamps (CTA 0, us):", np.round(tr[0, lay:lay + 22] / 1e3, 2))
+print("stamps per layer:", len(layer))
 eng.close()
