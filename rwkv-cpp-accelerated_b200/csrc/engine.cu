@@ -786,6 +786,8 @@ int rwkv_b200_set_option(rwkv_b200_model *m, const char *key, const char *value)
     } else if (k == "poll_first") {
         if (v < 0 || v > 2) return fail(1, "poll_first is 0, 1 or 2");
         m->p.poll_first = v;
+    } else if (k == "dbg") {
+        m->p.dbg = v;
     } else if (k == "timeout_ms") {
         if (v < 1) return fail(1, "timeout_ms must be positive");
         m->p.timeout_ms = (unsigned int)v;
