@@ -696,7 +696,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_token(const __grid_constant__ P
     auto slice_to_att = [&](int l) {
         const uint32_t ep = p.ep0 + 1u + (uint32_t)l;
         double xmean, rstd;
-        if (p.dbg & 1) { // debug: the same code once more beforehand (on the other buffer, already complete): cold vs warm
+        if ((p.dbg & 1) && l > 0) { // debug: the same code once more beforehand (on the other buffer, already complete): cold vs warm
             double cd = c0;
             slice_stats(p, sm, stat1, ne, ep - 1u, (unsigned int)l, ctid, cd, xmean, rstd, c_trace);
         }

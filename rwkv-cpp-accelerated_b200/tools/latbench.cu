@@ -1,0 +1,138 @@
+// latbench.cu — ground-truth latencies of the building blocks of the token kernel's phase boundaries on the
+// actual GPU, one warp, with the token kernel's shared-memory carve-out (227 KB -> almost no L1).
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o latbench latbench.cu && ./latbench
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ double wsum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_relaxed(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// a large body of straight-line dependent code (cold I-cache the first time)
+template <int N> __device__ __noinline__ double cold_code(double x, double y) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        x = fma(x, 1.0000001, y);
+        y = fma(y, 0.9999999, x * 1e-9);
+    }
+    return x + y;
+}
+
+__global__ void k_lat(unsigned long long *buf, long long *out, double *dout, int iters) {
+    extern __shared__ unsigned char smem[];
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x >= 32) return;
+    long long t0, t1;
+    double acc = (double)lane;
+    // 1. %globaltimer read
+    unsigned long long g = 0;
+    t0 = clock64();
+    for (int i = 0; i < 16; ++i) g ^= gtimer();
+    t1 = clock64();
+    if (lane == 0) out[0] = (t1 - t0) / 16;
+    // 2. double shuffle-reduce (5 steps)
+    t0 = clock64();
+    for (int i = 0; i < 16; ++i) acc = wsum(acc) * 0.03125;
+    t1 = clock64();
+    if (lane == 0) out[1] = (t1 - t0) / 16;
+    // 3. L2 round trip: dependent relaxed loads (pointer chase over 64 slots, 128-byte stride)
+    unsigned long long idx = lane;
+    t0 = clock64();
+    for (int i = 0; i < 16; ++i) idx = ld_relaxed(buf + (idx & 63) * 16);
+    t1 = clock64();
+    if (lane == 0) out[2] = (t1 - t0) / 16;
+    // 4. store -> load of the same address (relaxed, gpu scope)
+    t0 = clock64();
+    for (int i = 0; i < 16; ++i) {
+        st_relaxed(buf + 2048 + lane, idx + i);
+        idx += ld_relaxed(buf + 2048 + lane) & 1;
+    }
+    t1 = clock64();
+    if (lane == 0) out[3] = (t1 - t0) / 16;
+    // 5. local memory round trip (dynamic index defeats register promotion)
+    {
+        volatile double loc[32];
+        for (int i = 0; i < 32; ++i) loc[i] = acc + i;
+        int j = (int)(idx & 31);
+        t0 = clock64();
+        for (int i = 0; i < 16; ++i) j = ((int)loc[j] + i) & 31;
+        t1 = clock64();
+        if (lane == 0) out[4] = (t1 - t0) / 16;
+        acc += j;
+    }
+    // 6. cold vs warm straight-line code: 2048 dependent DFMA pairs (~64 KB of SASS)
+    t0 = clock64();
+    acc = cold_code<2048>(acc, 1.0);
+    t1 = clock64();
+    if (lane == 0) out[5] = t1 - t0;
+    t0 = clock64();
+    acc = cold_code<2048>(acc, 1.0);
+    t1 = clock64();
+    if (lane == 0) out[6] = t1 - t0;
+    // 7. a small cold function vs warm (96 DFMA pairs ~ 3 KB)
+    t0 = clock64();
+    acc = cold_code<96>(acc, 1.0);
+    t1 = clock64();
+    if (lane == 0) out[7] = t1 - t0;
+    t0 = clock64();
+    acc = cold_code<96>(acc, 1.0);
+    t1 = clock64();
+    if (lane == 0) out[8] = t1 - t0;
+    // 8. double division, exp
+    t0 = clock64();
+    for (int i = 0; i < 16; ++i) acc = 1.0 / (acc + 1.5);
+    t1 = clock64();
+    if (lane == 0) out[9] = (t1 - t0) / 16;
+    t0 = clock64();
+    for (int i = 0; i < 16; ++i) acc = exp(acc * 0.5);
+    t1 = clock64();
+    if (lane == 0) out[10] = (t1 - t0) / 16;
+    // 9. globaltimer resolution: ns between two distinct values
+    unsigned long long a = gtimer(), b2;
+    do { b2 = gtimer(); } while (b2 == a);
+    if (lane == 0) out[11] = (long long)(b2 - a);
+    dout[lane] = acc + (double)g + (double)idx + smem[lane];
+}
+
+int main() {
+    unsigned long long *buf;
+    long long *out, h[16] = {0};
+    double *dout;
+    cudaMalloc(&buf, 1 << 20);
+    cudaMalloc(&out, 16 * 8);
+    cudaMalloc(&dout, 32 * 8);
+    unsigned long long hb[64 * 16];
+    for (int i = 0; i < 64 * 16; ++i) hb[i] = (unsigned long long)((i / 16) * 7 + 3);
+    cudaMemcpy(buf, hb, sizeof(hb), cudaMemcpyHostToDevice);
+    cudaFuncSetAttribute(k_lat, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    for (int rep = 0; rep < 2; ++rep) {
+        k_lat<<<1, 64, 232448>>>(buf, out, dout, 16);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) {
+            printf("error: %s\n", cudaGetErrorString(e));
+            return 1;
+        }
+        cudaMemcpy(h, out, sizeof(h), cudaMemcpyDeviceToHost);
+        printf("run %d (SM cycles): globaltimer read %lld | f64 warp-sum %lld | L2 dependent load %lld | st+ld same addr %lld | "
+               "local mem round trip %lld | 64KB code cold %lld warm %lld | 3KB code cold %lld warm %lld | ddiv %lld | exp %lld | "
+               "globaltimer tick %lld ns\n",
+               rep, h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8], h[9], h[10], h[11]);
+    }
+    return 0;
+}
