@@ -421,10 +421,18 @@ __device__ __noinline__ void slice_stats(const Params &p, const Smem &sm, Tagged
         const double v0 = lane < ne ? sm.xown[lane] : 0.0, v1 = lane + 32 < ne ? sm.xown[lane + 32] : 0.0;
         const double d0 = lane < ne ? v0 - c0 : 0.0, d1 = lane + 32 < ne ? v1 - c0 : 0.0;
         double s = v0 + v1, q = d0 * d0 + d1 * d1;
+        if ((p.dbg & 2) && trace != nullptr) { // debug: split the segment
+            if (__double_as_longlong(q) == 0x7ff8000000000001ll) s = 0.0; // (consume q before the stamp)
+            trace_stamp(trace, sm.scal, ctid);
+        }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { // two independent trees, interleaved
             s += __shfl_xor_sync(0xffffffffu, s, o);
             q += __shfl_xor_sync(0xffffffffu, q, o);
+        }
+        if ((p.dbg & 2) && trace != nullptr) {
+            if (__double_as_longlong(q) == 0x7ff8000000000001ll) s = 0.0;
+            trace_stamp(trace, sm.scal, ctid);
         }
         if (lane == 0) {
             st_tagged_double(&sums[blockIdx.x], s, tag, false);
