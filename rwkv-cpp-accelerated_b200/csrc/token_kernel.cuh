@@ -364,6 +364,7 @@ __device__ __forceinline__ void gather(const Params &p, const Smem &sm, const fl
         else if (gg < 2 * ng) mx1 = max(mx1, m);
         else mx2 = max(mx2, m);
     }
+    __syncwarp();
     mx0 = __reduce_max_sync(0xffffffffu, mx0);
     mx1 = __reduce_max_sync(0xffffffffu, mx1);
     mx2 = __reduce_max_sync(0xffffffffu, mx2);
@@ -421,9 +422,11 @@ __device__ __noinline__ void slice_stats(const Params &p, const Smem &sm, Tagged
         const double v0 = lane < ne ? sm.xown[lane] : 0.0, v1 = lane + 32 < ne ? sm.xown[lane + 32] : 0.0;
         const double d0 = lane < ne ? v0 - c0 : 0.0, d1 = lane + 32 < ne ? v1 - c0 : 0.0;
         double s = v0 + v1, q = d0 * d0 + d1 * d1;
+        __syncwarp(); // reconverge (see warp_sum in common.cuh)
         if ((p.dbg & 2) && trace != nullptr) { // debug: split the segment
             if (__double_as_longlong(q) == 0x7ff8000000000001ll) s = 0.0; // (consume q before the stamp)
             trace_stamp(trace, sm.scal, ctid);
+            __syncwarp();
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { // two independent trees, interleaved
@@ -434,6 +437,7 @@ __device__ __noinline__ void slice_stats(const Params &p, const Smem &sm, Tagged
             if (__double_as_longlong(q) == 0x7ff8000000000001ll) s = 0.0;
             trace_stamp(trace, sm.scal, ctid);
         }
+        __syncwarp();
         if (lane == 0) {
             st_tagged_double(&sums[blockIdx.x], s, tag, false);
             st_tagged_double(&qs[blockIdx.x], q, tag, false);
@@ -480,6 +484,7 @@ __device__ __noinline__ void slice_stats(const Params &p, const Smem &sm, Tagged
             st += pair_to_double(a[i], b[i]);
             qt += pair_to_double(c[i], d[i]);
         }
+        __syncwarp();
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             st += __shfl_xor_sync(0xffffffffu, st, o);
@@ -937,6 +942,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_token(const __grid_constant__ P
             }
             if (p.greedy) {
                 // block arg-max, first index wins ties
+                __syncwarp();
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
                     const float ov2 = __shfl_xor_sync(0xffffffffu, best, o);
@@ -983,6 +989,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_token(const __grid_constant__ P
                             i2 = ix;
                         }
                     }
+                    __syncwarp();
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) {
                         const float ov2 = __shfl_xor_sync(0xffffffffu, b2, o);
