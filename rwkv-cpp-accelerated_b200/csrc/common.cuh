@@ -196,6 +196,12 @@ __device__ __forceinline__ size_t opaque(size_t v) {
     return v;
 }
 
+// clock read that the compiler keeps between the computation of `a`, `b` and everything that uses them afterwards
+__device__ __forceinline__ long long clock_after(double &a, double &b) {
+    long long t;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t), "+d"(a), "+d"(b));
+    return t;
+}
 __device__ __forceinline__ void tok_sync() { // named barrier 1: the eight consumer warps
     asm volatile("bar.sync 1, %0;" ::"n"(kConsumers) : "memory");
 }
@@ -232,10 +238,11 @@ struct Smem {
     double *pd;          // [kMaxSlice][8] epilogue parameters of the slice owners, staged with cp.async
     float *pf;           // [kMaxSlice][8]
     float *pk;           // [kMaxKeys][2]  ffn-V scale / offset of the own key channels
+    long long *clk;      // [16] debug cycle counters (set_option dbg=4)
 };
 
 __host__ __device__ inline size_t smem_fixed_bytes() {
-    return kMaxRowsPerCta * 8 + 16 * 8 + kWarps * 4 * 4 + 2 * kMaxStages * 8 + kMaxSlice * (8 + 4 + 64 + 32) + kMaxKeys * 8 + 128;
+    return kMaxRowsPerCta * 8 + 16 * 8 + kWarps * 4 * 4 + 2 * kMaxStages * 8 + kMaxSlice * (8 + 4 + 64 + 32) + kMaxKeys * 8 + 128 + 128;
 }
 __host__ __device__ inline size_t smem_bytes(int stages, int tile_bytes, int plane_cap) {
     return (size_t)stages * tile_bytes + plane_cap + smem_fixed_bytes();
@@ -266,6 +273,8 @@ __device__ __forceinline__ Smem carve(uint8_t *base, const Params &p) {
     s.srown = reinterpret_cast<float *>(q);
     q += kMaxSlice * sizeof(float);
     s.wmax = reinterpret_cast<uint32_t *>(q);
+    q += kWarps * 4 * sizeof(uint32_t);
+    s.clk = reinterpret_cast<long long *>(q);
     return s;
 }
 

@@ -423,6 +423,9 @@ __device__ __noinline__ void slice_stats(const Params &p, const Smem &sm, Tagged
         const double d0 = lane < ne ? v0 - c0 : 0.0, d1 = lane + 32 < ne ? v1 - c0 : 0.0;
         double s = v0 + v1, q = d0 * d0 + d1 * d1;
         __syncwarp(); // reconverge (see warp_sum in common.cuh)
+        const bool clk = (p.dbg & 4) != 0;
+        long long tc0 = 0, tc1 = 0, tc2 = 0, tc3 = 0, tc4 = 0;
+        if (clk) tc0 = clock_after(s, q);
         if ((p.dbg & 2) && trace != nullptr) { // debug: split the segment
             if (__double_as_longlong(q) == 0x7ff8000000000001ll) s = 0.0; // (consume q before the stamp)
             trace_stamp(trace, sm.scal, ctid);
@@ -437,6 +440,7 @@ __device__ __noinline__ void slice_stats(const Params &p, const Smem &sm, Tagged
             if (__double_as_longlong(q) == 0x7ff8000000000001ll) s = 0.0;
             trace_stamp(trace, sm.scal, ctid);
         }
+        if (clk) tc1 = clock_after(s, q);
         __syncwarp();
         if (lane == 0) {
             st_tagged_double(&sums[blockIdx.x], s, tag, false);
@@ -484,11 +488,23 @@ __device__ __noinline__ void slice_stats(const Params &p, const Smem &sm, Tagged
             st += pair_to_double(a[i], b[i]);
             qt += pair_to_double(c[i], d[i]);
         }
+        if (clk) tc2 = clock_after(st, qt);
         __syncwarp();
+        if (clk) tc3 = clock_after(st, qt);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             st += __shfl_xor_sync(0xffffffffu, st, o);
             qt += __shfl_xor_sync(0xffffffffu, qt, o);
+        }
+        if (clk) {
+            tc4 = clock_after(st, qt);
+            if (lane == 0) {
+                sm.clk[0] += tc1 - tc0; // first pair of trees
+                sm.clk[1] += tc2 - tc1; // publish + records
+                sm.clk[2] += tc3 - tc2; // __syncwarp
+                sm.clk[3] += tc4 - tc3; // second pair of trees
+                sm.clk[4] += 1;
+            }
         }
         if (lane == 0) {
             const double Ed = (double)p.E;
@@ -608,8 +624,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_token(const __grid_constant__ P
     if (ctid == 0) {
         *reinterpret_cast<int *>(sm.scal + 8) = 0;
         *reinterpret_cast<int *>(sm.scal + 9) = 0;
+        for (int i = 0; i < 16; ++i) sm.clk[i] = 0;
     }
-    unsigned long long *const c_trace = TRACE ? p.trace : nullptr;
+    unsigned long long *const c_trace = (TRACE && !(p.dbg & 4)) ? p.trace : nullptr;
     auto stamp = [&]() {
         if (TRACE) trace_stamp(c_trace, sm.scal, ctid);
     };
@@ -1040,6 +1057,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_token(const __grid_constant__ P
         }
     }
     if (blockIdx.x == 0 && ctid == 0 && p.feed_mode == 2) p.ctrl->pos = p.ctrl->pos + 1;
+    if ((p.dbg & 4) && p.trace != nullptr && ctid == 0)
+        for (int i = 0; i < 16; ++i) p.trace[(size_t)blockIdx.x * kTraceMax + i] = (unsigned long long)sm.clk[i];
     stamp();
 }
 

@@ -136,3 +136,94 @@ int main() {
     }
     return 0;
 }
+
+// ---- part 2: the same f64 warp-sum inside the token kernel's environment, one ingredient at a time ---------------
+// flags: 1 = 7 more warps blocked on a named barrier; 2 = a lane of warp 8 spinning on mbarrier.try_wait;
+//        4 = setmaxnreg (consumers 232 / producer 40); 8 = bulk copies global->shared in flight (ring of 4 x 32 KB)
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__global__ void __launch_bounds__(384, 1) k_env(const unsigned char *src, long long *out, double *dout, int flags) {
+    extern __shared__ __align__(128) unsigned char smem2[];
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem2 + 200000);
+    volatile int *stop = reinterpret_cast<volatile int *>(smem2 + 200064);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(1));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar + 1)), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        *stop = 0;
+    }
+    __syncthreads();
+    if (warp >= 8) {
+        if (flags & 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        if (warp == 8 && lane == 0) {
+            if (flags & 8) { // stream 32 KB tiles into a 4-stage ring, no consumer: wait for each to land, go on
+                uint32_t parity = 0;
+                size_t off = 0;
+                while (!*stop) {
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar + 1)), "r"(32768) : "memory");
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(smem2)),
+                                 "l"(src + off), "r"(32768), "r"(smem_addr(bar + 1))
+                                 : "memory");
+                    uint32_t ok = 0;
+                    while (!ok) {
+                        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_addr(bar + 1)), "r"(parity) : "memory");
+                    }
+                    parity ^= 1;
+                    off = (off + 32768 * 148) & ((1ull << 30) - 1);
+                }
+            } else if (flags & 2) { // spin on a barrier nobody completes
+                uint32_t ok = 0;
+                while (!ok && !*stop) {
+                    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_addr(bar)), "r"(0) : "memory");
+                }
+            }
+        }
+        return;
+    }
+    if (flags & 4) asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    if (warp > 0) {
+        if (flags & 1) asm volatile("bar.sync 1, 256;" ::: "memory");
+        return;
+    }
+    // warp 0: let the others settle, then time
+    long long t0 = clock64();
+    while (clock64() - t0 < 20000) {}
+    double acc = (double)lane;
+    t0 = clock64();
+    for (int i = 0; i < 16; ++i) acc = wsum(acc) * 0.03125;
+    long long t1 = clock64();
+    // diverge (lane 0 does extra work), then sum again without and with __syncwarp
+    if (lane == 0) acc += (double)(clock64() & 1);
+    long long t2 = clock64();
+    for (int i = 0; i < 16; ++i) acc = wsum(acc) * 0.03125;
+    long long t3 = clock64();
+    if (lane == 0) {
+        out[0] = (t1 - t0) / 16;
+        out[1] = (t3 - t2) / 16;
+    }
+    dout[lane] = acc;
+    *stop = 1;
+    if (flags & 1) asm volatile("bar.sync 1, 256;" ::: "memory");
+}
+
+struct Part2 {
+    Part2() {
+        unsigned char *src;
+        long long *out, h[2];
+        double *dout;
+        cudaMalloc(&src, (1ull << 30) + (1 << 20));
+        cudaMalloc(&out, 16);
+        cudaMalloc(&dout, 256);
+        cudaFuncSetAttribute(k_env, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+        for (int flags : {0, 1, 2, 3, 4, 7, 8, 9, 15}) {
+            k_env<<<148, 384, 232448>>>(src, out, dout, flags);
+            cudaError_t e = cudaDeviceSynchronize();
+            if (e != cudaSuccess) {
+                printf("flags %d error: %s\n", flags, cudaGetErrorString(e));
+                break;
+            }
+            cudaMemcpy(h, out, sizeof(h), cudaMemcpyDeviceToHost);
+            printf("env flags %2d: f64 warp-sum %lld cycles, after a lane-0 branch %lld cycles\n", flags, h[0], h[1]);
+        }
+    }
+} part2_runs_before_main_returns;
