@@ -499,11 +499,12 @@ __device__ __noinline__ void slice_stats(const Params &p, const Smem &sm, Tagged
         if (clk) {
             tc4 = clock_after(st, qt);
             if (lane == 0) {
-                sm.clk[0] += tc1 - tc0; // first pair of trees
-                sm.clk[1] += tc2 - tc1; // publish + records
-                sm.clk[2] += tc3 - tc2; // __syncwarp
-                sm.clk[3] += tc4 - tc3; // second pair of trees
-                sm.clk[4] += 1;
+                long long *ck = sm.clk + ((layer & 0x8000u) ? 8 : 0); // the debug "cold" call counts separately
+                ck[0] += tc1 - tc0; // first pair of trees
+                ck[1] += tc2 - tc1; // publish + records
+                ck[2] += tc3 - tc2; // __syncwarp
+                ck[3] += tc4 - tc3; // second pair of trees
+                ck[4] += 1;
             }
         }
         if (lane == 0) {
@@ -728,7 +729,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_token(const __grid_constant__ P
         double xmean, rstd;
         if ((p.dbg & 1) && l > 0) { // debug: the same code once more beforehand (on the other buffer, already complete): cold vs warm
             double cd = c0;
-            slice_stats(p, sm, stat1, ne, ep - 1u, (unsigned int)l, ctid, cd, xmean, rstd, c_trace);
+            slice_stats(p, sm, stat1, ne, ep - 1u, (unsigned int)l | 0x8000u, ctid, cd, xmean, rstd, c_trace);
         }
         slice_stats(p, sm, stat0, ne, ep, (unsigned int)l, ctid, c0, xmean, rstd, c_trace);
         stamp();
@@ -886,7 +887,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_token(const __grid_constant__ P
                 double xmean, rstd;
                 if (p.dbg & 1) {
                     double cd = c0;
-                    slice_stats(p, sm, stat0, ne, ep, (unsigned int)l, ctid, cd, xmean, rstd, c_trace);
+                    slice_stats(p, sm, stat0, ne, ep, (unsigned int)l | 0x8000u, ctid, cd, xmean, rstd, c_trace);
                 }
                 slice_stats(p, sm, stat1, ne, ep, (unsigned int)l, ctid, c0, xmean, rstd, c_trace);
                 stamp();

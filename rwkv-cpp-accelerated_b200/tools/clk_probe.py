@@ -7,7 +7,7 @@ import bench  # noqa: E402
 pkg = importlib.import_module("rwkv-cpp-accelerated_b200")
 eng = pkg.Engine(bench.model_path(sys.argv[1] if len(sys.argv) > 1 else "7b", pkg))
 eng.set_option("trace", 1)
-eng.set_option("dbg", 4)
+eng.set_option("dbg", int(os.environ.get("DBG", "4")))
 for kv in sys.argv[2:]:
     k, v = kv.split("=")
     eng.set_option(k, v)
@@ -20,4 +20,10 @@ for i, nm in enumerate(["first trees", "publish+records", "syncwarp", "second tr
     per = tr[:, i] / n
     print("%-16s cycles per call: mean %.0f min %.0f max %.0f" % (nm, per.mean(), per.min(), per.max()))
 print("calls per token", n.mean())
+tr = eng.read_trace().astype(np.int64)[:, :16]
+n = tr[:, 12].clip(1)
+for i, nm in enumerate(["first trees", "publish+records", "syncwarp", "second trees"]):
+    per = tr[:, 8 + i] / n
+    print("cold call: %-16s cycles per call: mean %.0f min %.0f max %.0f" % (nm, per.mean(), per.min(), per.max()))
+print("cold calls per token", tr[:, 12].mean())
 eng.close()
