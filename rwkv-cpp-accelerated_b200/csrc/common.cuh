@@ -29,6 +29,7 @@ constexpr int kMaxGrid = 160;              // CTAs per rank (one per SM)
 constexpr int kMaxRanks = 8;
 constexpr int kMaxSlice = 64;              // residual elements / channels one CTA owns
 constexpr int kMaxKeys = 160;              // ffn key channels one CTA owns
+constexpr int kRep = 8;                    // replicas of the per-CTA exchange records (readers of one L2 line / kRep)
 constexpr int kMaxRowsPerCta = 1024;       // res64 capacity (rows x segments of one CTA)
 constexpr int kTraceMax = 2048;            // trace stamps per CTA (debug)
 constexpr int kTileTraceMax = 4096;        // tiles per CTA recorded by the tile trace (debug)
@@ -102,8 +103,8 @@ struct Params {
     // The exchange block of this rank (one allocation, peer-mapped by the other ranks). Offsets are the
     // same on every rank: xch[g] + off is rank g's copy as seen from here (xch[rank] = the local one).
     unsigned char *xch[kMaxRanks];
-    unsigned int off_stat[2];   // [2][grid] tagged doubles: slice sums, slice M2 (LN1 / LN_out, LN2)
-    unsigned int off_off[5];    // [3][grid] tagged doubles: partial offset sums per vector (kvr, out, rk, v, head)
+    unsigned int off_stat[2];   // [kRep][2][grid] tagged doubles: slice sums, slice Q (LN1 / LN_out, LN2)
+    unsigned int off_off[5];    // [kRep][3][grid] tagged doubles: partial offset sums per vector (kvr, out, rk, v, head)
     unsigned int off_vec[5];    // f32+tag vectors (kvr 3E, out Er, rk 2E, v 4Er, head E)
     unsigned int off_in[2];     // [G][E] tagged doubles: partial sums from every rank (out-proj, ffn-V)
     unsigned int off_sr;        // [E] tagged f32: sigmoid(ffn r) of every channel

@@ -290,6 +290,7 @@ __device__ __forceinline__ void gather(const Params &p, const Smem &sm, const fl
             f[0] = ld_vec4(s0);
         }
     }
+    __syncwarp();
 #pragma unroll
     for (int i = 1; i < kGatherMax; ++i) {
         f[i] = absent;
@@ -301,6 +302,7 @@ __device__ __forceinline__ void gather(const Params &p, const Smem &sm, const fl
         const int lane = ctid & 31;
         constexpr int kPer = (kMaxGrid + 31) / 32;
         const unsigned long long none = tag64(0u, tag);
+        const TaggedDouble *const orec = offrec + (size_t)(blockIdx.x % kRep) * 3 * gridDim.x; // this CTA's replica
         unsigned long long a[3][kPer], b[3][kPer];
 #pragma unroll
         for (int v = 0; v < 3; ++v) {
@@ -308,7 +310,7 @@ __device__ __forceinline__ void gather(const Params &p, const Smem &sm, const fl
             for (int i = 0; i < kPer; ++i) {
                 a[v][i] = none;
                 b[v][i] = none;
-                if (v < nvec && lane + 32 * i < (int)gridDim.x) ld_pair(&offrec[v * (int)gridDim.x + lane + 32 * i], a[v][i], b[v][i], false);
+                if (v < nvec && lane + 32 * i < (int)gridDim.x) ld_pair(&orec[v * (int)gridDim.x + lane + 32 * i], a[v][i], b[v][i], false);
             }
         }
         for (;;) {
@@ -318,12 +320,12 @@ __device__ __forceinline__ void gather(const Params &p, const Smem &sm, const fl
 #pragma unroll
                 for (int i = 0; i < kPer; ++i) {
                     if (!tags_ok(a[v][i], b[v][i], tag)) {
-                        ld_pair(&offrec[v * (int)gridDim.x + lane + 32 * i], a[v][i], b[v][i], false);
+                        ld_pair(&orec[v * (int)gridDim.x + lane + 32 * i], a[v][i], b[v][i], false);
                         bad = true;
                     }
                 }
             }
-            if (!bad) break;
+            if (!__any_sync(0xffffffffu, bad)) break; // warp-uniform exit (see slice_stats)
             if (waiter_tick(p, wt)) wait_expired(p, kDiagOff, layer, (unsigned int)nvec, tag, (unsigned int)(a[0][0] >> 32), (unsigned long long)lane);
         }
         double sv[3];
@@ -350,7 +352,7 @@ __device__ __forceinline__ void gather(const Params &p, const Smem &sm, const fl
                 bad = true;
             }
         }
-        if (!bad) break;
+        if (!__any_sync(0xffffffffu, bad)) break; // warp-uniform exit (see slice_stats)
         if (waiter_tick(p, wt)) wait_expired(p, kDiagVec, layer, (unsigned int)nvec, tag2, 99u, (unsigned long long)base);
     }
     trace_stamp(trace, sm.scal, ctid); // all words here
@@ -418,7 +420,9 @@ __device__ __noinline__ void slice_stats(const Params &p, const Smem &sm, Tagged
     if (ctid < 32) {
         const int lane = ctid;
         const int nb = (int)gridDim.x;
-        TaggedDouble *const sums = recs, *const qs = recs + nb; // [nb] each
+        // Every CTA reads every record: 148 x 32 lanes on the same few L2 lines serialise there (measured 1.6 us
+        // for one batch of loads). The writer stores kRep copies, reader b takes copy b % kRep.
+        TaggedDouble *const sums = recs + (size_t)(blockIdx.x % kRep) * 2 * nb, *const qs = sums + nb; // [nb] each
         const double v0 = lane < ne ? sm.xown[lane] : 0.0, v1 = lane + 32 < ne ? sm.xown[lane + 32] : 0.0;
         const double d0 = lane < ne ? v0 - c0 : 0.0, d1 = lane + 32 < ne ? v1 - c0 : 0.0;
         double s = v0 + v1, q = d0 * d0 + d1 * d1;
@@ -442,9 +446,9 @@ __device__ __noinline__ void slice_stats(const Params &p, const Smem &sm, Tagged
         }
         if (clk) tc1 = clock_after(s, q);
         __syncwarp();
-        if (lane == 0) {
-            st_tagged_double(&sums[blockIdx.x], s, tag, false);
-            st_tagged_double(&qs[blockIdx.x], q, tag, false);
+        if (lane < kRep) {
+            st_tagged_double(&recs[(size_t)lane * 2 * nb + blockIdx.x], s, tag, false);
+            st_tagged_double(&recs[(size_t)lane * 2 * nb + nb + blockIdx.x], q, tag, false);
         }
         trace_stamp(trace, sm.scal, ctid); // S2: own record published
         // every CTA's record: all in flight at once (r = lane, lane+32, ...), re-read what has not arrived
@@ -478,7 +482,9 @@ __device__ __noinline__ void slice_stats(const Params &p, const Smem &sm, Tagged
                     bad = true;
                 }
             }
-            if (!bad) break;
+            // warp-uniform exit: lanes that leave a loop at different iterations stay split, and a split warp
+            // pays ~100 cycles for every shuffle afterwards, __syncwarp() or not (measured: 1850 vs 260 cycles)
+            if (!__any_sync(0xffffffffu, bad)) break;
             if (waiter_tick(p, w)) wait_expired(p, kDiagStats, layer, 0, tag, (unsigned int)(a[0] >> 32), (unsigned long long)lane);
         }
         trace_stamp(trace, sm.scal, ctid); // S4: every record here
@@ -550,9 +556,13 @@ __device__ __forceinline__ void publish_offsums(const Smem &sm, TaggedDouble *re
             }
         }
     }
-    if (ctid == 0) {
+    if (w == 0) { // lane r stores replica r: [kRep][3][grid]
+        __syncwarp();
 #pragma unroll
-        for (int k = 0; k < NV; ++k) st_tagged_double(&recs[k * (int)gridDim.x + blockIdx.x], of[k], tag, false); // [NV][grid]
+        for (int k = 0; k < NV; ++k) {
+            const double v = __shfl_sync(0xffffffffu, of[k], 0);
+            if ((ctid & 31) < kRep) st_tagged_double(&recs[((size_t)(ctid & 31) * 3 + k) * gridDim.x + blockIdx.x], v, tag, false);
+        }
     }
 }
 
