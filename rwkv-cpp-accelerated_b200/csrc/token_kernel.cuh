@@ -236,14 +236,20 @@ __device__ __forceinline__ void quantize4(const uint4 f, float inv, uint8_t *pla
 }
 
 // ---- debug tracing --------------------------------------------------------------------------------------
+// Executed by the whole of warp 0 with predicated stores: a branch taken by lane 0 alone would split the warp,
+// and a split warp pays ~100 cycles for every later shuffle (the first version of this function made the
+// reductions that followed a stamp look 10x slower than they are).
 __device__ __forceinline__ void trace_stamp(unsigned long long *trace, double *scal, int ctid) {
-    if (trace != nullptr && ctid == 0) {
-        int *cnt = reinterpret_cast<int *>(scal + 8);
-        const int c = *cnt;
-        if (c < kTraceMax) {
-            trace[(size_t)blockIdx.x * kTraceMax + c] = globaltimer();
-            *cnt = c + 1;
-        }
+    if (trace != nullptr && ctid < 32) {
+        const uint32_t cnt = smem_u32(scal + 8);
+        int c;
+        asm volatile("ld.shared.s32 %0, [%1];" : "=r"(c) : "r"(cnt) : "memory");
+        const unsigned long long t = globaltimer();
+        unsigned long long *dst = trace + (size_t)blockIdx.x * kTraceMax + (c < kTraceMax ? c : kTraceMax - 1);
+        __syncwarp(); // every lane has read the counter
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %0, 0;\n\t@p st.global.u64 [%1], %2;\n\t@p st.shared.s32 [%3], %4;\n\t}"
+                     ::"r"(ctid), "l"(dst), "l"(t), "r"(cnt), "r"(c < kTraceMax ? c + 1 : c)
+                     : "memory");
     }
 }
 
@@ -464,11 +470,7 @@ __device__ __noinline__ void slice_stats(const Params &p, const Smem &sm, Tagged
             }
         }
         Waiter w = waiter_begin();
-        if (trace != nullptr && ctid == 0) { // S3: first answers back (forces a wait on the loads)
-            volatile unsigned long long sink = a[0] ^ c[kPer - 1];
-            (void)sink;
-        }
-        trace_stamp(trace, sm.scal, ctid);
+        trace_stamp(trace, sm.scal, ctid); // S3: loads issued
         for (;;) {
             bool bad = false;
 #pragma unroll
