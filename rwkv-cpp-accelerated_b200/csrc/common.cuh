@@ -75,6 +75,7 @@ struct Params {
     int greedy;             // 1: finish with an on-device argmax into ctrl->next
     int issue_gap;          // minimum SM cycles between two bulk-copy issues of the producer (0 = unpaced)
     int window;             // bulk copies in flight per CTA (<= stages)
+    int pf_dist;            // tiles the L2 prefetch cursor runs ahead of the ring (0 = no L2 prefetch)
     int dbg;                // debug experiments (bit 0: run the slice statistics twice, cold / warm code)
     int poll_first;         // gather: 1 = poll the first 16 bytes before fetching the rest, 0 = fetch everything at once
     unsigned int ep0;       // epoch before this token: layer l tags its exchanges with ep0 + 1 + l

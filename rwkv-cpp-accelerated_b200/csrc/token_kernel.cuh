@@ -68,15 +68,97 @@ __host__ __device__ inline Slices make_slices(int E, int Er, int Vr, int b, int 
 // Weights are row-major [out][in] int8. A tile is exactly eight work units; a unit is one row segment
 // (rows of <= E bytes: one unit per row, eight rows per tile; ffn-V rows of 4*Er bytes: four units per
 // row, two rows per tile), so consumer warp w always takes unit w of every tile.
+//
+// The schedule of one CTA is a fixed sequence of tiles: per layer the subs K, V, R (own channels), out-proj
+// (own slice), ffn-R (own channels), ffn-K (own key channels), ffn-V (own slice), then the head rows. Two
+// cursors walk it: `cp` issues the bulk copies into the ring (bounded by free stages and by `window` copies in
+// flight), `pf` runs `pf_dist` tiles further ahead and only asks L2 to fetch the bytes
+// (cp.async.bulk.prefetch.L2). The shared-memory ring holds at most 3.7 us of HBM time; a phase boundary
+// takes longer than that, so without the second cursor HBM idles in every boundary and the following phase
+// starts from an empty pipe. With it HBM streams continuously into L2 (126 MB) and the ring refills from
+// L2 at the consumers' pace.
+struct TileCursor {
+    int l, s;           // layer (== L_run: head), sub inside the layer
+    int r, nr, tr;      // next row inside the sub, rows of the sub, rows per tile
+    int N;              // bytes per row
+    const int8_t *base; // first row of the sub
+};
+struct TileRef {
+    const int8_t *ptr;
+    uint32_t bytes;
+};
+// Sub `s` of layer `l` -> cursor fields (base pointer of the own rows, bytes per row, rows per tile, row count).
+__device__ __noinline__ void load_sub(const Params &p, const Slices &sl, TileCursor &c) {
+    const int E = p.E, Er = p.Er;
+    c.r = 0;
+    if (c.l >= p.L_run) {
+        c.N = E; c.tr = 8; c.nr = c.l == p.L_run ? sl.nv : 0;
+        c.base = p.whead + (size_t)sl.v0 * E;
+        return;
+    }
+    const size_t mc = (size_t)c.l * Er * E; // one column-split matrix [Er][E]
+    switch (c.s) {
+    case 0: c.N = E; c.tr = 8; c.nr = sl.nc; c.base = p.wk + mc + (size_t)sl.c0 * E; break;
+    case 1: c.N = E; c.tr = 8; c.nr = sl.nc; c.base = p.wv + mc + (size_t)sl.c0 * E; break;
+    case 2: c.N = E; c.tr = 8; c.nr = sl.nc; c.base = p.wr + mc + (size_t)sl.c0 * E; break;
+    case 3: c.N = Er; c.tr = 8; c.nr = sl.ne; c.base = p.wo + mc + (size_t)sl.e0 * Er; break;
+    case 4: c.N = E; c.tr = 8; c.nr = sl.nc; c.base = p.wfr + mc + (size_t)sl.c0 * E; break;
+    case 5: c.N = E; c.tr = 8; c.nr = sl.nk; c.base = p.wfk + 4 * mc + (size_t)sl.k0 * E; break;
+    default: c.N = 4 * Er; c.tr = 2; c.nr = sl.ne; c.base = p.wfv + 4 * mc + (size_t)sl.e0 * 4 * Er; break;
+    }
+}
+// The tile under the cursor, then advance. Returns false at the end of the token's schedule.
+__device__ __forceinline__ bool next_tile(const Params &p, const Slices &sl, TileCursor &c, TileRef &t) {
+    while (c.r >= c.nr) { // next sub
+        if (c.l >= p.L_run) {
+            if (c.l > p.L_run) return false;
+            ++c.l; // past the head: the end
+            c.nr = 0;
+            return false;
+        }
+        if (++c.s == 7) {
+            c.s = 0;
+            ++c.l;
+        }
+        load_sub(p, sl, c);
+    }
+    t.ptr = c.base + (size_t)c.r * c.N;
+    t.bytes = (uint32_t)(min(c.tr, c.nr - c.r) * c.N);
+    c.r += c.tr;
+    return true;
+}
+
 // `window`: at most that many bulk copies of this CTA are in flight (issued, not landed). The memory
 // system serves the SMs' copies in order, so everything in flight queues AHEAD of the small latency-
-// critical loads of an exchange: 5 x 32 KB per SM is 3.7 us of queue at the HBM rate, two tiles are
-// enough to keep HBM saturated. The ring still holds `stages` landed tiles.
-__device__ __forceinline__ void produce_sub(const Params &p, uint32_t ring, uint32_t full0, uint32_t empty0,
-                                            const int8_t *base, int N, int tr, int r0, int nr, RingPos &rp, RingPos &wp,
-                                            uint64_t policy, int &tcount, unsigned long long *ptrace, long long &last_issue) {
-    for (int r = 0; r < nr; r += tr) {
-        const uint32_t bytes = (uint32_t)(min(tr, nr - r) * N);
+// critical loads of an exchange: 5 x 32 KB per SM is 3.7 us of queue at the HBM rate.
+template <bool TRACE>
+__device__ __forceinline__ void produce_token(const Params &p, const Smem &sm, const Slices &sl) {
+    unsigned long long *const ptrace = TRACE ? p.ptrace : nullptr;
+    // evict_first keeps the weight stream from displacing the exchange words and the per-layer
+    // parameters in L2 (measured in round 1: evict_normal costs 15 %).
+    const uint64_t pol = policy_evict_first();
+    const uint32_t ring = smem_u32(sm.ring), full0 = smem_u32(sm.full), empty0 = smem_u32(sm.empty);
+    RingPos rp{0, 0}, wp{0, 0};
+    TileCursor cp, pf;
+    cp.l = 0;
+    cp.s = 0;
+    load_sub(p, sl, cp);
+    pf = cp;
+    bool pf_live = true;
+    int tcount = 0, ahead = 0; // tiles issued; tiles the prefetch cursor is in front of the copy cursor
+    long long last_issue = 0;
+    TileRef t;
+    for (;;) {
+        while (pf_live && ahead < p.pf_dist + 1) { // keep L2 `pf_dist` tiles ahead of the ring
+            TileRef q;
+            pf_live = next_tile(p, sl, pf, q);
+            if (!pf_live) break;
+            if (p.pf_dist > 0 && ahead >= 1) // (the tile the copy cursor takes next is fetched by the copy itself)
+                asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(q.ptr), "r"(q.bytes), "l"(pol) : "memory");
+            ++ahead;
+        }
+        if (!next_tile(p, sl, cp, t)) break;
+        --ahead;
         if (tcount >= p.window) { // tile (tcount - window) must have landed
             mbar_wait(p, full0 + 8 * wp.stage, wp.phase, kDiagRingFull);
             wp.advance((uint32_t)p.stages);
@@ -88,37 +170,12 @@ __device__ __forceinline__ void produce_sub(const Params &p, uint32_t ring, uint
             last_issue = clock64();
         }
         const uint32_t fb = full0 + 8 * rp.stage;
-        mbar_expect_tx(fb, bytes);
-        bulk_g2s(ring + rp.stage * (uint32_t)p.tile_bytes, base + (size_t)(r0 + r) * N, bytes, fb, policy);
+        mbar_expect_tx(fb, t.bytes);
+        bulk_g2s(ring + rp.stage * (uint32_t)p.tile_bytes, t.ptr, t.bytes, fb, pol);
         if (ptrace != nullptr && tcount < kTileTraceMax) ptrace[(size_t)blockIdx.x * kTileTraceMax + tcount] = globaltimer();
         ++tcount;
         rp.advance((uint32_t)p.stages);
     }
-}
-
-// The producer's whole-token schedule. MUST enumerate subs in exactly the consumers' order.
-template <bool TRACE>
-__device__ __forceinline__ void produce_token(const Params &p, const Smem &sm, const Slices &sl) {
-    unsigned long long *const ptrace = TRACE ? p.ptrace : nullptr;
-    // evict_first keeps the weight stream from displacing the exchange words and the per-layer
-    // parameters in L2 (measured in round 1: evict_normal costs 15 %).
-    const uint64_t pol = policy_evict_first();
-    const int E = p.E, Er = p.Er;
-    const uint32_t ring = smem_u32(sm.ring), full0 = smem_u32(sm.full), empty0 = smem_u32(sm.empty);
-    RingPos rp{0, 0}, wp{0, 0};
-    int tcount = 0;
-    long long last_issue = 0;
-    for (int l = 0; l < p.L_run; ++l) {
-        const size_t mc = (size_t)l * Er * E; // column-split matrices [Er][E]
-        produce_sub(p, ring, full0, empty0, p.wk + mc, E, 8, sl.c0, sl.nc, rp, wp, pol, tcount, ptrace, last_issue);
-        produce_sub(p, ring, full0, empty0, p.wv + mc, E, 8, sl.c0, sl.nc, rp, wp, pol, tcount, ptrace, last_issue);
-        produce_sub(p, ring, full0, empty0, p.wr + mc, E, 8, sl.c0, sl.nc, rp, wp, pol, tcount, ptrace, last_issue);
-        produce_sub(p, ring, full0, empty0, p.wo + mc, Er, 8, sl.e0, sl.ne, rp, wp, pol, tcount, ptrace, last_issue);
-        produce_sub(p, ring, full0, empty0, p.wfr + mc, E, 8, sl.c0, sl.nc, rp, wp, pol, tcount, ptrace, last_issue);
-        produce_sub(p, ring, full0, empty0, p.wfk + 4 * mc, E, 8, sl.k0, sl.nk, rp, wp, pol, tcount, ptrace, last_issue);
-        produce_sub(p, ring, full0, empty0, p.wfv + 4 * mc, 4 * Er, 2, sl.e0, sl.ne, rp, wp, pol, tcount, ptrace, last_issue);
-    }
-    produce_sub(p, ring, full0, empty0, p.whead, E, 8, sl.v0, sl.nv, rp, wp, pol, tcount, ptrace, last_issue);
 }
 
 // ---- consumer core -----------------------------------------------------------------------------------
