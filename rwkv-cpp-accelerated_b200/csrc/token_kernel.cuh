@@ -87,8 +87,9 @@ struct TileRef {
     const int8_t *ptr;
     uint32_t bytes;
 };
+// (inlined: the producer warp runs with 40 registers after setmaxnreg; a separately compiled function does not know that)
 // Sub `s` of layer `l` -> cursor fields (base pointer of the own rows, bytes per row, rows per tile, row count).
-__device__ __noinline__ void load_sub(const Params &p, const Slices &sl, TileCursor &c) {
+__device__ __forceinline__ void load_sub(const Params &p, const Slices &sl, TileCursor &c) {
     const int E = p.E, Er = p.Er;
     c.r = 0;
     if (c.l >= p.L_run) {
