@@ -155,7 +155,9 @@ __device__ __forceinline__ void produce_token(const Params &p, const Smem &sm, c
             pf_live = next_tile(p, sl, pf, q);
             if (!pf_live) break;
             if (p.pf_dist > 0 && ahead >= 1) // (the tile the copy cursor takes next is fetched by the copy itself)
-                asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(q.ptr), "r"(q.bytes), "l"(pol) : "memory");
+                // default L2 policy: with evict_first the stream of newer prefetches evicts the oldest ones - the tiles
+                // about to be consumed; the consuming copy then marks the lines evict_first
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(q.ptr), "r"(q.bytes) : "memory");
             ++ahead;
         }
         if (!next_tile(p, sl, cp, t)) break;
