@@ -106,6 +106,7 @@ struct Params {
     unsigned char *xch[kMaxRanks];
     unsigned int off_stat[2];   // [kRep][2][grid] tagged doubles: slice sums, slice Q (LN1 / LN_out, LN2)
     unsigned int off_off[5];    // [kRep][3][grid] tagged doubles: partial offset sums per vector (kvr, out, rk, v, head)
+    unsigned int off_max[5];    // [kRep][3][grid] tagged f32: slice max |xs| per vector
     unsigned int off_vec[5];    // f32+tag vectors (kvr 3E, out Er, rk 2E, v 4Er, head E)
     unsigned int off_in[2];     // [G][E] tagged doubles: partial sums from every rank (out-proj, ffn-V)
     unsigned int off_sr;        // [E] tagged f32: sigmoid(ffn r) of every channel
@@ -241,10 +242,11 @@ struct Smem {
     float *pf;           // [kMaxSlice][8]
     float *pk;           // [kMaxKeys][2]  ffn-V scale / offset of the own key channels
     long long *clk;      // [16] debug cycle counters (set_option dbg=4)
+    float *ginv;         // [4] 1 / S of the vectors of the current gather
 };
 
 __host__ __device__ inline size_t smem_fixed_bytes() {
-    return kMaxRowsPerCta * 8 + 16 * 8 + kWarps * 4 * 4 + 2 * kMaxStages * 8 + kMaxSlice * (8 + 4 + 64 + 32) + kMaxKeys * 8 + 128 + 128;
+    return kMaxRowsPerCta * 8 + 16 * 8 + kWarps * 4 * 4 + 2 * kMaxStages * 8 + kMaxSlice * (8 + 4 + 64 + 32) + kMaxKeys * 8 + 128 + 128 + 16;
 }
 __host__ __device__ inline size_t smem_bytes(int stages, int tile_bytes, int plane_cap) {
     return (size_t)stages * tile_bytes + plane_cap + smem_fixed_bytes();
@@ -277,6 +279,8 @@ __device__ __forceinline__ Smem carve(uint8_t *base, const Params &p) {
     s.wmax = reinterpret_cast<uint32_t *>(q);
     q += kWarps * 4 * sizeof(uint32_t);
     s.clk = reinterpret_cast<long long *>(q);
+    q += 16 * sizeof(long long);
+    s.ginv = reinterpret_cast<float *>(q);
     return s;
 }
 

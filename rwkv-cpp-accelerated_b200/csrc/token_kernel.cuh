@@ -325,7 +325,8 @@ __device__ __forceinline__ void trace_stamp(unsigned long long *trace, double *s
 // Inlined ONCE (the phase loop of the kernel has a single call site): as a separate function it would be
 // compiled against the 168-register launch budget instead of the consumers' 232 and spill.
 constexpr int kGatherMax = 20; // 16-byte groups per thread: 256 x 20 x 4 >= 4 * 5120
-__device__ __forceinline__ void gather(const Params &p, const Smem &sm, const float *vec, const TaggedDouble *offrec, int nvec,
+__device__ __forceinline__ void gather(const Params &p, const Smem &sm, const float *vec, const TaggedDouble *offrec,
+                                       const unsigned long long *maxrec, int nvec,
                                        int N, uint32_t tag, unsigned int layer, int ctid, unsigned long long *trace) {
     const uint32_t tag2 = tag & 3u;
     const int ng = N >> 2;        // groups per vector
@@ -369,14 +370,19 @@ __device__ __forceinline__ void gather(const Params &p, const Smem &sm, const fl
         constexpr int kPer = (kMaxGrid + 31) / 32;
         const unsigned long long none = tag64(0u, tag);
         const TaggedDouble *const orec = offrec + (size_t)(blockIdx.x % kRep) * 3 * gridDim.x; // this CTA's replica
-        unsigned long long a[3][kPer], b[3][kPer];
+        const unsigned long long *const mrec = maxrec + (size_t)(blockIdx.x % kRep) * 3 * gridDim.x;
+        unsigned long long a[3][kPer], b[3][kPer], m[3][kPer];
 #pragma unroll
         for (int v = 0; v < 3; ++v) {
 #pragma unroll
             for (int i = 0; i < kPer; ++i) {
                 a[v][i] = none;
                 b[v][i] = none;
-                if (v < nvec && lane + 32 * i < (int)gridDim.x) ld_pair(&orec[v * (int)gridDim.x + lane + 32 * i], a[v][i], b[v][i], false);
+                m[v][i] = none;
+                if (v < nvec && lane + 32 * i < (int)gridDim.x) {
+                    ld_pair(&orec[v * (int)gridDim.x + lane + 32 * i], a[v][i], b[v][i], false);
+                    m[v][i] = ld_word(&mrec[v * (int)gridDim.x + lane + 32 * i], false);
+                }
             }
         }
         for (;;) {
@@ -389,23 +395,34 @@ __device__ __forceinline__ void gather(const Params &p, const Smem &sm, const fl
                         ld_pair(&orec[v * (int)gridDim.x + lane + 32 * i], a[v][i], b[v][i], false);
                         bad = true;
                     }
+                    if ((uint32_t)(m[v][i] >> 32) != tag) {
+                        m[v][i] = ld_word(&mrec[v * (int)gridDim.x + lane + 32 * i], false);
+                        bad = true;
+                    }
                 }
             }
             if (!__any_sync(0xffffffffu, bad)) break; // warp-uniform exit (see slice_stats)
             if (waiter_tick(p, wt)) wait_expired(p, kDiagOff, layer, (unsigned int)nvec, tag, (unsigned int)(a[0][0] >> 32), (unsigned long long)lane);
         }
         double sv[3];
+        uint32_t mv[3];
 #pragma unroll
         for (int v = 0; v < 3; ++v) {
             double t = 0.0;
+            uint32_t mm = 0u;
 #pragma unroll
-            for (int i = 0; i < kPer; ++i) t += pair_to_double(a[v][i], b[v][i]);
+            for (int i = 0; i < kPer; ++i) {
+                t += pair_to_double(a[v][i], b[v][i]);
+                mm = max(mm, (uint32_t)m[v][i]);
+            }
             sv[v] = warp_sum(t);
+            mv[v] = __reduce_max_sync(0xffffffffu, mm);
         }
-        if (lane == 0) {
-            sm.scal[3] = sv[0];
-            sm.scal[4] = sv[1];
-            sm.scal[5] = sv[2];
+        if (lane < 3) { // lane v: scale of vector v (IEEE division: the same bits in every CTA)
+            const float mf = __uint_as_float(lane == 0 ? mv[0] : lane == 1 ? mv[1] : mv[2]);
+            sm.scal[lane] = (double)mf * (1.0 / (double)kQMax);
+            sm.scal[3 + lane] = lane == 0 ? sv[0] : lane == 1 ? sv[1] : sv[2];
+            sm.ginv[lane] = mf > 0.0f ? (float)kQMax / mf : 0.0f;
         }
     }
     // late words: re-read until every group carries the tag
@@ -422,39 +439,10 @@ __device__ __forceinline__ void gather(const Params &p, const Smem &sm, const fl
         if (waiter_tick(p, wt)) wait_expired(p, kDiagVec, layer, (unsigned int)nvec, tag2, 99u, (unsigned long long)base);
     }
     trace_stamp(trace, sm.scal, ctid); // all words here
-    // per-vector max |xs| (bit patterns of non-negative floats order like unsigned integers)
-    uint32_t mx0 = 0u, mx1 = 0u, mx2 = 0u;
-#pragma unroll
-    for (int i = 0; i < kGatherMax; ++i) {
-        const int gg = index(i);
-        const uint32_t m = max(max(f[i].x & 0x7ffffffcu, f[i].y & 0x7ffffffcu), max(f[i].z & 0x7ffffffcu, f[i].w & 0x7ffffffcu));
-        if (gg < ng) mx0 = max(mx0, m);
-        else if (gg < 2 * ng) mx1 = max(mx1, m);
-        else mx2 = max(mx2, m);
-    }
-    __syncwarp();
-    mx0 = __reduce_max_sync(0xffffffffu, mx0);
-    mx1 = __reduce_max_sync(0xffffffffu, mx1);
-    mx2 = __reduce_max_sync(0xffffffffu, mx2);
-    if ((ctid & 31) == 0) {
-        uint32_t *wm = sm.wmax + (ctid >> 5) * 4;
-        wm[0] = mx0;
-        wm[1] = mx1;
-        wm[2] = mx2;
-    }
-    trace_stamp(trace, sm.scal, ctid); // G3: own maxima written
-    tok_sync();
-    trace_stamp(trace, sm.scal, ctid); // G4: all warps (incl. the offset sums of warp 7) done
-    float inv[3];
-#pragma unroll
-    for (int v = 0; v < 3; ++v) {
-        uint32_t m = 0u;
-#pragma unroll
-        for (int w = 0; w < kWarps; ++w) m = max(m, sm.wmax[w * 4 + v]);
-        const float mf = __uint_as_float(m);
-        inv[v] = mf > 0.0f ? (float)kQMax / mf : 0.0f; // IEEE division: the same bits in every CTA
-        if (ctid == v) sm.scal[v] = (double)mf * (1.0 / (double)kQMax);
-    }
+    trace_stamp(trace, sm.scal, ctid); // G3
+    tok_sync(); // scales and offset sums of warp 7 are in shared memory
+    trace_stamp(trace, sm.scal, ctid); // G4
+    const float inv[3] = {sm.ginv[0], sm.ginv[1], sm.ginv[2]};
 #pragma unroll
     for (int i = 0; i < kGatherMax; ++i) {
         if (i < cnt) {
@@ -594,36 +582,48 @@ __device__ __noinline__ void slice_stats(const Params &p, const Smem &sm, Tagged
     c0 = xmean;
 }
 
-// Partial offset sums of this CTA (data in the first `nact` consumer threads, NV values each) -> its
-// OffRec. Fixed reduction shape: shuffle tree per warp, then warps 0..nw-1 in order. Called by every
-// consumer warp; warps without data return at once. (NV > 1 only for slice owners: <= 2 warps.)
+// Partial offset sums and the largest |xs| of this CTA's slice (data in the first `nact` consumer threads, NV
+// values each) -> its records. Fixed reduction shape: shuffle tree per warp, then warps 0..nw-1 in order.
+// Called by every consumer warp; warps without data return at once. (NV > 1 only for slice owners: <= 2 warps.)
+// mx: bit patterns of non-negative floats (they order like unsigned integers).
 template <int NV>
-__device__ __forceinline__ void publish_offsums(const Smem &sm, TaggedDouble *recs, double (&of)[NV], uint32_t tag, int ctid, int nact) {
+__device__ __forceinline__ void publish_slice(const Smem &sm, TaggedDouble *recs, unsigned long long *mrecs, double (&of)[NV],
+                                              uint32_t (&mx)[NV], uint32_t tag, int ctid, int nact) {
     const int nw = nact > 0 ? (nact + 31) >> 5 : 1; // an empty slice still publishes zeros
     const int w = ctid >> 5;
     if (w >= nw) return;
 #pragma unroll
-    for (int k = 0; k < NV; ++k) of[k] = warp_sum(of[k]);
+    for (int k = 0; k < NV; ++k) {
+        of[k] = warp_sum(of[k]);
+        mx[k] = __reduce_max_sync(0xffffffffu, mx[k]);
+    }
     double *scr = sm.scal + 10; // [nw - 1][NV] <= 6 doubles
+    uint32_t *mscr = sm.wmax;   // [kWarps][4]
     if (nw > 1) {
         if ((ctid & 31) == 0 && w > 0) {
 #pragma unroll
-            for (int k = 0; k < NV; ++k) scr[(w - 1) * NV + k] = of[k];
+            for (int k = 0; k < NV; ++k) {
+                scr[(w - 1) * NV + k] = of[k];
+                mscr[w * 4 + k] = mx[k];
+            }
         }
         asm volatile("bar.sync 3, %0;" ::"r"(nw * 32) : "memory");
-        if (ctid == 0) {
+        if (w == 0) { // every lane of warp 0 adds the other warps' parts in the same order
             for (int i = 1; i < nw; ++i) {
 #pragma unroll
-                for (int k = 0; k < NV; ++k) of[k] += scr[(i - 1) * NV + k];
+                for (int k = 0; k < NV; ++k) {
+                    of[k] += scr[(i - 1) * NV + k];
+                    mx[k] = max(mx[k], mscr[i * 4 + k]);
+                }
             }
         }
     }
-    if (w == 0) { // lane r stores replica r: [kRep][3][grid]
-        __syncwarp();
+    if (w == 0 && (ctid & 31) < kRep) { // lane r stores replica r: [kRep][3][grid]
 #pragma unroll
         for (int k = 0; k < NV; ++k) {
-            const double v = __shfl_sync(0xffffffffu, of[k], 0);
-            if ((ctid & 31) < kRep) st_tagged_double(&recs[((size_t)(ctid & 31) * 3 + k) * gridDim.x + blockIdx.x], v, tag, false);
+            const size_t at = ((size_t)(ctid & 31) * 3 + k) * gridDim.x + blockIdx.x;
+            st_tagged_double(&recs[at], of[k], tag, false);
+            st_word(&mrecs[at], tag64(mx[k], tag), false);
         }
     }
 }
@@ -809,6 +809,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_token(const __grid_constant__ P
         if (l < p.L_run) {
             float *const vec_kvr = reinterpret_cast<float *>(xl + p.off_vec[0]);
             double of[3] = {0, 0, 0};
+            uint32_t mx[3] = {0u, 0u, 0u};
             if (mine) {
                 const uint32_t t2 = ep & 3u;
                 const double mk = pd[2], mv = pd[3], mr = pd[4], st = pd[5];
@@ -819,26 +820,31 @@ __global__ void __launch_bounds__(kThreads, 1) k_token(const __grid_constant__ P
                 const float xk = (float)((double)fk * (double)pf[0]);
                 const float xv = (float)((double)fv * (double)pf[1]);
                 const float xr = (float)((double)fr * (double)pf[2]);
-                st_f32(vec_kvr + j, tag_f32(xk, t2));
-                st_f32(vec_kvr + E + j, tag_f32(xv, t2));
-                st_f32(vec_kvr + 2 * E + j, tag_f32(xr, t2));
+                const uint32_t bk = tag_f32(xk, t2), bv = tag_f32(xv, t2), br = tag_f32(xr, t2);
+                st_f32(vec_kvr + j, bk);
+                st_f32(vec_kvr + E + j, bv);
+                st_f32(vec_kvr + 2 * E + j, br);
+                mx[0] = bk & 0x7ffffffcu; mx[1] = bv & 0x7ffffffcu; mx[2] = br & 0x7ffffffcu;
                 of[0] = (double)fk * (double)pf[3];
                 of[1] = (double)fv * (double)pf[4];
                 of[2] = (double)fr * (double)pf[5];
                 p.sxy[so + (size_t)l * E + j] = ln; // only the owner ever reads or writes this element
             }
-            publish_offsums<3>(sm, reinterpret_cast<TaggedDouble *>(xl + p.off_off[0]), of, ep, ctid, ne);
+            publish_slice<3>(sm, reinterpret_cast<TaggedDouble *>(xl + p.off_off[0]), reinterpret_cast<unsigned long long *>(xl + p.off_max[0]), of, mx, ep, ctid, ne);
         } else {
             float *const vec_h = reinterpret_cast<float *>(xl + p.off_vec[4]);
             double of[1] = {0};
+            uint32_t mx[1] = {0u};
             if (mine) {
                 const float f = (float)(pd[0] * ((sm.xown[ctid] - xmean) * rstd) + pd[1]);
                 const float xh = (float)((double)f * (double)pf[0]);
-                st_f32(vec_h + j, tag_f32(xh, p.tk & 3u));
+                const uint32_t bh = tag_f32(xh, p.tk & 3u);
+                st_f32(vec_h + j, bh);
+                mx[0] = bh & 0x7ffffffcu;
                 of[0] = (double)f * (double)pf[1];
                 p.x[j] = sm.xown[ctid]; // residual stream after the last layer (debug / tests)
             }
-            publish_offsums<1>(sm, reinterpret_cast<TaggedDouble *>(xl + p.off_off[4]), of, p.tk, ctid, ne);
+            publish_slice<1>(sm, reinterpret_cast<TaggedDouble *>(xl + p.off_off[4]), reinterpret_cast<unsigned long long *>(xl + p.off_max[4]), of, mx, p.tk, ctid, ne);
         }
         stamp();
     };
@@ -868,6 +874,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_token(const __grid_constant__ P
         }
         const float *vec = reinterpret_cast<const float *>(xl + p.off_vec[ph]);
         const TaggedDouble *offrec = reinterpret_cast<const TaggedDouble *>(xl + p.off_off[ph]);
+        const unsigned long long *maxrec = reinterpret_cast<const unsigned long long *>(xl + p.off_max[ph]);
         // -------- park the epilogue's parameters in shared memory ------------------------------------
         if (ph == 0) {
             if (owner_warps) { // WKV of channel cg (clamped: an idle thread reads a valid address)
@@ -901,7 +908,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_token(const __grid_constant__ P
             if (owner_warps) fetch_ln1(l + 1);
         }
         // -------- gather + stream ------------------------------------------------------------------
-        gather(p, sm, vec, offrec, nvec, N, tag, (unsigned int)l, ctid, c_trace);
+        gather(p, sm, vec, offrec, maxrec, nvec, N, tag, (unsigned int)l, ctid, c_trace);
         {
             const bool exact = FULL && N == (nseg == 4 ? 4 * E : E); // segment == CPL * 512 bytes
             uint32_t planes = c_planes, res = c_res;
@@ -921,6 +928,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_token(const __grid_constant__ P
             // ======== WKV for the own channels (rwkv.cu:544-545) -> rwkv * r_out =========================
             if (owner_warps) {
                 double of[1] = {0};
+                uint32_t mx[1] = {0u};
                 if (minec) {
                     const double aa = pd[0], bb = pd[1], wd = pd[2], ub = pd[3], ew = pd[4]; // exp(decay) is static: tabulated at load
                     const float kf = (float)(sm.scal[0] * row_total(0, ctid, 1) + sm.scal[3]);
@@ -940,10 +948,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_token(const __grid_constant__ P
                     }
                     const float rw = (float)y;
                     const float xo = (float)((double)rw * (double)pf[0]);
-                    st_f32(reinterpret_cast<float *>(xl + p.off_vec[1]) + cl, tag_f32(xo, ep & 3u));
+                    const uint32_t bo = tag_f32(xo, ep & 3u);
+                    st_f32(reinterpret_cast<float *>(xl + p.off_vec[1]) + cl, bo);
+                    mx[0] = bo & 0x7ffffffcu;
                     of[0] = (double)rw * (double)pf[1];
                 }
-                publish_offsums<1>(sm, reinterpret_cast<TaggedDouble *>(xl + p.off_off[1]), of, ep, ctid, nc);
+                publish_slice<1>(sm, reinterpret_cast<TaggedDouble *>(xl + p.off_off[1]), reinterpret_cast<unsigned long long *>(xl + p.off_max[1]), of, mx, ep, ctid, nc);
             }
         } else if (ph == 1) {
             // ======== residual (rwkv.cu:548-553), then LN2 + token shift (557-562) ========================
@@ -964,6 +974,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_token(const __grid_constant__ P
                 slice_stats(p, sm, stat1, ne, ep, (unsigned int)l, ctid, c0, xmean, rstd, c_trace);
                 stamp();
                 double of[2] = {0, 0};
+                uint32_t mx[2] = {0u, 0u};
                 if (mine) {
                     const double fmk = pd[2], fmr = pd[3], fst = pd[4];
                     const double ln = pd[0] * ((sm.xown[ctid] - xmean) * rstd) + pd[1];
@@ -972,13 +983,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_token(const __grid_constant__ P
                     const float xr = (float)((double)fr * (double)pf[0]);
                     const float xk = (float)((double)fk * (double)pf[1]);
                     float *const vec_rk = reinterpret_cast<float *>(xl + p.off_vec[2]);
-                    st_f32(vec_rk + j, tag_f32(xr, ep & 3u));
-                    st_f32(vec_rk + E + j, tag_f32(xk, ep & 3u));
+                    const uint32_t br = tag_f32(xr, ep & 3u), bk = tag_f32(xk, ep & 3u);
+                    st_f32(vec_rk + j, br);
+                    st_f32(vec_rk + E + j, bk);
+                    mx[0] = br & 0x7ffffffcu; mx[1] = bk & 0x7ffffffcu;
                     of[0] = (double)fr * (double)pf[2];
                     of[1] = (double)fk * (double)pf[3];
                     p.sdd[so + lo + j] = ln;
                 }
-                publish_offsums<2>(sm, reinterpret_cast<TaggedDouble *>(xl + p.off_off[2]), of, ep, ctid, ne);
+                publish_slice<2>(sm, reinterpret_cast<TaggedDouble *>(xl + p.off_off[2]), reinterpret_cast<unsigned long long *>(xl + p.off_max[2]), of, mx, ep, ctid, ne);
             }
         } else if (ph == 2) {
             // ======== sigmoid(ffn r) for the own channels, relu^2 of the own key channels (566-573) =======
@@ -990,15 +1003,18 @@ __global__ void __launch_bounds__(kThreads, 1) k_token(const __grid_constant__ P
                     for (int g = 0; g < p.G; ++g) st_word(xch_at<unsigned long long>(p, g, p.off_sr) + cg, tag64(__float_as_uint(sr), ep), true);
             }
             double of[1] = {0};
+            uint32_t mx[1] = {0u};
             if (minek) {
                 float a = (float)(sm.scal[1] * row_total(nc, ctid, 1) + sm.scal[4]);
                 a = a > 0.0f ? a : 0.0f;
                 a = a * a;
                 const float xv = (float)((double)a * (double)pk[0]);
-                st_f32(reinterpret_cast<float *>(xl + p.off_vec[3]) + sl.k0 + ctid, tag_f32(xv, ep & 3u));
+                const uint32_t bv = tag_f32(xv, ep & 3u);
+                st_f32(reinterpret_cast<float *>(xl + p.off_vec[3]) + sl.k0 + ctid, bv);
+                mx[0] = bv & 0x7ffffffcu;
                 of[0] = (double)a * (double)pk[1];
             }
-            publish_offsums<1>(sm, reinterpret_cast<TaggedDouble *>(xl + p.off_off[3]), of, ep, ctid, nk);
+            publish_slice<1>(sm, reinterpret_cast<TaggedDouble *>(xl + p.off_off[3]), reinterpret_cast<unsigned long long *>(xl + p.off_max[3]), of, mx, ep, ctid, nk);
         } else if (ph == 3) {
             // ======== residual (rwkv.cu:574-577), then the next layer's LN1 (or LN_out) ====================
             if (owner_warps) {
