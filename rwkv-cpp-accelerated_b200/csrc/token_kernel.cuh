@@ -285,14 +285,18 @@ __device__ __forceinline__ RingPos consume_sub(const Params &p, uint32_t ring, u
 __device__ __forceinline__ uint32_t round_q(float xs, float inv) {
     return __float_as_uint(fmaf(xs, inv, 12582912.0f)) - 0x4B400000u;
 }
-__device__ __forceinline__ void quantize4(const uint4 f, float inv, uint8_t *planes, int stride, int j) {
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+// `plane0`: shared-window address of the element's word in limb plane 0; planes 1, 2 are `stride` bytes apart
+__device__ __forceinline__ void quantize4(const uint4 f, float inv, uint32_t plane0, uint32_t stride) {
     const uint32_t t0 = round_q(untag_f32(f.x), inv), t1 = round_q(untag_f32(f.y), inv);
     const uint32_t t2 = round_q(untag_f32(f.z), inv), t3 = round_q(untag_f32(f.w), inv);
     const uint32_t lo01 = __byte_perm(t0, t1, 0x5140), lo23 = __byte_perm(t2, t3, 0x5140);
     const uint32_t hi01 = __byte_perm(t0, t1, 0x0062), hi23 = __byte_perm(t2, t3, 0x0062);
-    *reinterpret_cast<uint32_t *>(planes + j) = __byte_perm(lo01, lo23, 0x5410);
-    *reinterpret_cast<uint32_t *>(planes + stride + j) = __byte_perm(lo01, lo23, 0x7632);
-    *reinterpret_cast<uint32_t *>(planes + 2 * stride + j) = __byte_perm(hi01, hi23, 0x5410);
+    sts32(plane0, __byte_perm(lo01, lo23, 0x5410));
+    sts32(plane0 + stride, __byte_perm(lo01, lo23, 0x7632));
+    sts32(plane0 + 2 * stride, __byte_perm(hi01, hi23, 0x5410));
 }
 
 // ---- debug tracing --------------------------------------------------------------------------------------
@@ -442,14 +446,16 @@ __device__ __forceinline__ void gather(const Params &p, const Smem &sm, const fl
     trace_stamp(trace, sm.scal, ctid); // G3
     tok_sync(); // scales and offset sums of warp 7 are in shared memory
     trace_stamp(trace, sm.scal, ctid); // G4
-    const float inv[3] = {sm.ginv[0], sm.ginv[1], sm.ginv[2]};
+    const float inv0 = sm.ginv[0], inv1 = sm.ginv[1], inv2 = sm.ginv[2];
+    const uint32_t pl0 = smem_u32(sm.planes);
 #pragma unroll
     for (int i = 0; i < kGatherMax; ++i) {
         if (i < cnt) {
+            // element 4*gg of the concatenated vectors sits 4*gg + v*2N bytes into the planes (3N bytes per vector)
             const int gg = index(i);
             const int v = (gg >= ng) + (gg >= 2 * ng);
-            const float iv = v == 0 ? inv[0] : v == 1 ? inv[1] : inv[2];
-            quantize4(f[i], iv, sm.planes + (size_t)v * 3 * N, N, 4 * (gg - v * ng));
+            const float iv = v == 0 ? inv0 : v == 1 ? inv1 : inv2;
+            quantize4(f[i], iv, pl0 + (uint32_t)(4 * gg + 2 * v * N), (uint32_t)N);
         }
     }
     tok_sync();
@@ -466,9 +472,16 @@ __device__ __forceinline__ void gather(const Params &p, const Smem &sm, const fl
 // xown holds the slice. The reader's work after the records arrive is two shuffle reductions and a dozen
 // scalar operations - this sits on the critical path of every layer twice.
 // Returns mean and 1 / sqrt(var) (unbiased, no epsilon); c0 is updated to the new mean.
-__device__ __noinline__ void slice_stats(const Params &p, const Smem &sm, TaggedDouble *recs, int ne, uint32_t tag,
-                                         unsigned int layer, int ctid, double &c0, double &xmean, double &rstd,
-                                         unsigned long long *trace) {
+struct StatsOut {
+    double mean, rstd;
+};
+__device__ __noinline__ StatsOut slice_stats(const Params &p, const double *xown, double *scal, long long *clkp, TaggedDouble *recs, int ne,
+                                             uint32_t tag, unsigned int layer, int ctid, double c0, unsigned long long *trace) {
+    struct {
+        const double *xown;
+        double *scal;
+        long long *clk;
+    } sm{xown, scal, clkp};
     own_sync(); // xown complete
     trace_stamp(trace, sm.scal, ctid); // S1: owners synchronised
     if (ctid < 32) {
@@ -577,9 +590,7 @@ __device__ __noinline__ void slice_stats(const Params &p, const Smem &sm, Tagged
         trace_stamp(trace, sm.scal, ctid); // S5: statistics computed
     }
     own_sync();
-    xmean = sm.scal[6];
-    rstd = sm.scal[7];
-    c0 = xmean;
+    return StatsOut{sm.scal[6], sm.scal[7]};
 }
 
 // Partial offset sums and the largest |xs| of this CTA's slice (data in the first `nact` consumer threads, NV
@@ -798,12 +809,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_token(const __grid_constant__ P
     // the last layer, LN_out -> publish the head input (rwkv.cu:585-588). Warps 0 and 1.
     auto slice_to_att = [&](int l) {
         const uint32_t ep = p.ep0 + 1u + (uint32_t)l;
-        double xmean, rstd;
-        if ((p.dbg & 1) && l > 0) { // debug: the same code once more beforehand (on the other buffer, already complete): cold vs warm
-            double cd = c0;
-            slice_stats(p, sm, stat1, ne, ep - 1u, (unsigned int)l | 0x8000u, ctid, cd, xmean, rstd, c_trace);
-        }
-        slice_stats(p, sm, stat0, ne, ep, (unsigned int)l, ctid, c0, xmean, rstd, c_trace);
+        const StatsOut so1 = slice_stats(p, sm.xown, sm.scal, sm.clk, stat0, ne, ep, (unsigned int)l, ctid, c0, c_trace);
+        const double xmean = so1.mean, rstd = so1.rstd;
+        c0 = xmean;
         stamp();
         cp_async_wait();
         if (l < p.L_run) {
@@ -966,12 +974,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_token(const __grid_constant__ P
                     sm.xown[ctid] = (double)xf;
                 }
                 stamp();
-                double xmean, rstd;
-                if (p.dbg & 1) {
-                    double cd = c0;
-                    slice_stats(p, sm, stat0, ne, ep, (unsigned int)l | 0x8000u, ctid, cd, xmean, rstd, c_trace);
-                }
-                slice_stats(p, sm, stat1, ne, ep, (unsigned int)l, ctid, c0, xmean, rstd, c_trace);
+                const StatsOut so2 = slice_stats(p, sm.xown, sm.scal, sm.clk, stat1, ne, ep, (unsigned int)l, ctid, c0, c_trace);
+                const double xmean = so2.mean, rstd = so2.rstd;
+                c0 = xmean;
                 stamp();
                 double of[2] = {0, 0};
                 uint32_t mx[2] = {0u, 0u};
