@@ -75,6 +75,7 @@ struct Params {
     int greedy;             // 1: finish with an on-device argmax into ctrl->next
     int issue_gap;          // minimum SM cycles between two bulk-copy issues of the producer (0 = unpaced)
     int window;             // bulk copies in flight per CTA (<= stages)
+    int bwindow;            // bulk copies in flight per CTA while the consumers exchange vectors (latency of their loads)
     int pf_dist;            // tiles the L2 prefetch cursor runs ahead of the ring (0 = no L2 prefetch)
     int dbg;                // debug experiments (bit 0: run the slice statistics twice, cold / warm code)
     int poll_first;         // gather: 1 = poll the first 16 bytes before fetching the rest, 0 = fetch everything at once
@@ -243,10 +244,12 @@ struct Smem {
     float *pk;           // [kMaxKeys][2]  ffn-V scale / offset of the own key channels
     long long *clk;      // [16] debug cycle counters (set_option dbg=4)
     float *ginv;         // [4] 1 / S of the vectors of the current gather
+    uint32_t *gmax;      // [4] max |xs| of the vectors of the current gather (atomicMax of the warps' parts), [3] boundary flag
+    double *osum;        // [kWarps][3] the warps' parts of the offset sums
 };
 
 __host__ __device__ inline size_t smem_fixed_bytes() {
-    return kMaxRowsPerCta * 8 + 16 * 8 + kWarps * 4 * 4 + 2 * kMaxStages * 8 + kMaxSlice * (8 + 4 + 64 + 32) + kMaxKeys * 8 + 128 + 128 + 16;
+    return kMaxRowsPerCta * 8 + 16 * 8 + kWarps * 4 * 4 + 2 * kMaxStages * 8 + kMaxSlice * (8 + 4 + 64 + 32) + kMaxKeys * 8 + 128 + 128 + 16 + 16 + kWarps * 3 * 8;
 }
 __host__ __device__ inline size_t smem_bytes(int stages, int tile_bytes, int plane_cap) {
     return (size_t)stages * tile_bytes + plane_cap + smem_fixed_bytes();
@@ -281,6 +284,10 @@ __device__ __forceinline__ Smem carve(uint8_t *base, const Params &p) {
     s.clk = reinterpret_cast<long long *>(q);
     q += 16 * sizeof(long long);
     s.ginv = reinterpret_cast<float *>(q);
+    q += 4 * sizeof(float);
+    s.gmax = reinterpret_cast<uint32_t *>(q);
+    q += 4 * sizeof(uint32_t);
+    s.osum = reinterpret_cast<double *>(q);
     return s;
 }
 

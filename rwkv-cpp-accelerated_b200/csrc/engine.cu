@@ -329,7 +329,8 @@ int do_load(M *m, const char *path, int quiet) {
     configure_ring(m);
     p.window = std::min(p.stages, 2);
     p.poll_first = 2;
-    p.pf_dist = 8;
+    p.pf_dist = 4;
+    p.bwindow = 1;
     if (p.stages < 2) return fail(5, "n_embed=%llu leaves no room for a two-stage ring", E);
     if (!grid_fits(E, Er, Vr, m->grid)) return fail(5, "a grid of %d CTAs does not fit n_embed=%llu", m->grid, E);
     const bool full = E == (unsigned long long)m->cpl * 512ull;
@@ -785,6 +786,9 @@ int rwkv_b200_set_option(rwkv_b200_model *m, const char *key, const char *value)
     } else if (k == "window") {
         if (v < 1 || v > rk::kMaxStages) return fail(1, "window must be 1..%d", rk::kMaxStages);
         m->p.window = v;
+    } else if (k == "bwindow") {
+        if (v < 1 || v > rk::kMaxStages) return fail(1, "bwindow must be 1..%d", rk::kMaxStages);
+        m->p.bwindow = v;
     } else if (k == "pf_dist") {
         if (v < 0 || v > 64) return fail(1, "pf_dist is 0..64 tiles");
         m->p.pf_dist = v;

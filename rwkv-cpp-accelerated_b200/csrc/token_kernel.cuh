@@ -146,7 +146,7 @@ __device__ __forceinline__ void produce_token(const Params &p, const Smem &sm, c
     load_sub(p, sl, cp);
     pf = cp;
     bool pf_live = true;
-    int tcount = 0, ahead = 0; // tiles issued; tiles the prefetch cursor is in front of the copy cursor
+    int tcount = 0, landed = 0, ahead = 0; // tiles issued; tiles known to have landed; lead of the prefetch cursor over the copy cursor
     long long last_issue = 0;
     TileRef t;
     for (;;) {
@@ -162,9 +162,14 @@ __device__ __forceinline__ void produce_token(const Params &p, const Smem &sm, c
         }
         if (!next_tile(p, sl, cp, t)) break;
         --ahead;
-        if (tcount >= p.window) { // tile (tcount - window) must have landed
+        // at most `window` copies in flight (`bwindow` while the consumers exchange vectors: everything this SM has
+        // in flight queues ahead of their loads, 0.75 us per 32 KB tile)
+        for (;;) {
+            const int win = *reinterpret_cast<volatile uint32_t *>(sm.gmax + 3) != 0u ? p.bwindow : p.window;
+            if (tcount - landed < win) break;
             mbar_wait(p, full0 + 8 * wp.stage, wp.phase, kDiagRingFull);
             wp.advance((uint32_t)p.stages);
+            ++landed;
         }
         // first pass over the ring: a fresh mbarrier reports the "previous" phase as complete
         mbar_wait(p, empty0 + 8 * rp.stage, rp.phase ^ 1, kDiagRingEmpty);
@@ -367,67 +372,44 @@ __device__ __forceinline__ void gather(const Params &p, const Smem &sm, const fl
         f[i] = absent;
         if (i < cnt) f[i] = ld_vec4(src + index(i));
     }
-    // partial offset sums of the owners (warp 7): all records in flight at once (lane r, r+32, ...), re-read
-    // what has not arrived, then add in ascending order and a fixed tree
-    if ((ctid >> 5) == kWarps - 1) {
-        const int lane = ctid & 31;
-        constexpr int kPer = (kMaxGrid + 31) / 32;
-        const unsigned long long none = tag64(0u, tag);
-        const TaggedDouble *const orec = offrec + (size_t)(blockIdx.x % kRep) * 3 * gridDim.x; // this CTA's replica
-        const unsigned long long *const mrec = maxrec + (size_t)(blockIdx.x % kRep) * 3 * gridDim.x;
-        unsigned long long a[3][kPer], b[3][kPer], m[3][kPer];
+    // The owners' records (partial offset sums, slice maxima), spread over the eight warps: warp w takes records
+    // w, w+8, ... (one per lane). Only the maxima are needed before the quantisation: one REDUX per vector and an
+    // atomicMax in shared memory; the f64 sums are reduced after the quantisation, off the critical path.
+    const int lane = ctid & 31, wq = ctid >> 5;
+    const int rec = wq + kWarps * lane;
+    const bool has_rec = rec < (int)gridDim.x;
+    const unsigned long long none = tag64(0u, tag);
+    const TaggedDouble *const orec = offrec + (size_t)(blockIdx.x % kRep) * 3 * gridDim.x + rec; // this CTA's replica
+    const unsigned long long *const mrec = maxrec + (size_t)(blockIdx.x % kRep) * 3 * gridDim.x + rec;
+    unsigned long long ra[3], rb[3], rm[3];
+#pragma unroll
+    for (int v = 0; v < 3; ++v) {
+        ra[v] = rb[v] = rm[v] = none;
+        if (has_rec && v < nvec) {
+            ld_pair(orec + v * (int)gridDim.x, ra[v], rb[v], false);
+            rm[v] = ld_word(mrec + v * (int)gridDim.x, false);
+        }
+    }
+    for (;;) {
+        bool bad = false;
 #pragma unroll
         for (int v = 0; v < 3; ++v) {
-#pragma unroll
-            for (int i = 0; i < kPer; ++i) {
-                a[v][i] = none;
-                b[v][i] = none;
-                m[v][i] = none;
-                if (v < nvec && lane + 32 * i < (int)gridDim.x) {
-                    ld_pair(&orec[v * (int)gridDim.x + lane + 32 * i], a[v][i], b[v][i], false);
-                    m[v][i] = ld_word(&mrec[v * (int)gridDim.x + lane + 32 * i], false);
-                }
+            if (!tags_ok(ra[v], rb[v], tag)) {
+                ld_pair(orec + v * (int)gridDim.x, ra[v], rb[v], false);
+                bad = true;
+            }
+            if ((uint32_t)(rm[v] >> 32) != tag) {
+                rm[v] = ld_word(mrec + v * (int)gridDim.x, false);
+                bad = true;
             }
         }
-        for (;;) {
-            bool bad = false;
+        if (!__any_sync(0xffffffffu, bad)) break; // warp-uniform exit (see slice_stats)
+        if (waiter_tick(p, wt)) wait_expired(p, kDiagOff, layer, (unsigned int)nvec, tag, (unsigned int)(ra[0] >> 32), (unsigned long long)rec);
+    }
 #pragma unroll
-            for (int v = 0; v < 3; ++v) {
-#pragma unroll
-                for (int i = 0; i < kPer; ++i) {
-                    if (!tags_ok(a[v][i], b[v][i], tag)) {
-                        ld_pair(&orec[v * (int)gridDim.x + lane + 32 * i], a[v][i], b[v][i], false);
-                        bad = true;
-                    }
-                    if ((uint32_t)(m[v][i] >> 32) != tag) {
-                        m[v][i] = ld_word(&mrec[v * (int)gridDim.x + lane + 32 * i], false);
-                        bad = true;
-                    }
-                }
-            }
-            if (!__any_sync(0xffffffffu, bad)) break; // warp-uniform exit (see slice_stats)
-            if (waiter_tick(p, wt)) wait_expired(p, kDiagOff, layer, (unsigned int)nvec, tag, (unsigned int)(a[0][0] >> 32), (unsigned long long)lane);
-        }
-        double sv[3];
-        uint32_t mv[3];
-#pragma unroll
-        for (int v = 0; v < 3; ++v) {
-            double t = 0.0;
-            uint32_t mm = 0u;
-#pragma unroll
-            for (int i = 0; i < kPer; ++i) {
-                t += pair_to_double(a[v][i], b[v][i]);
-                mm = max(mm, (uint32_t)m[v][i]);
-            }
-            sv[v] = warp_sum(t);
-            mv[v] = __reduce_max_sync(0xffffffffu, mm);
-        }
-        if (lane < 3) { // lane v: scale of vector v (IEEE division: the same bits in every CTA)
-            const float mf = __uint_as_float(lane == 0 ? mv[0] : lane == 1 ? mv[1] : mv[2]);
-            sm.scal[lane] = (double)mf * (1.0 / (double)kQMax);
-            sm.scal[3 + lane] = lane == 0 ? sv[0] : lane == 1 ? sv[1] : sv[2];
-            sm.ginv[lane] = mf > 0.0f ? (float)kQMax / mf : 0.0f;
-        }
+    for (int v = 0; v < 3; ++v) {
+        const uint32_t mm = __reduce_max_sync(0xffffffffu, (uint32_t)rm[v]);
+        if (lane == 0 && v < nvec) atomicMax(sm.gmax + v, mm);
     }
     // late words: re-read until every group carries the tag
     for (;;) {
@@ -444,9 +426,17 @@ __device__ __forceinline__ void gather(const Params &p, const Smem &sm, const fl
     }
     trace_stamp(trace, sm.scal, ctid); // all words here
     trace_stamp(trace, sm.scal, ctid); // G3
-    tok_sync(); // scales and offset sums of warp 7 are in shared memory
+    tok_sync(); // the maxima of all warps are in shared memory
     trace_stamp(trace, sm.scal, ctid); // G4
-    const float inv0 = sm.ginv[0], inv1 = sm.ginv[1], inv2 = sm.ginv[2];
+    if (ctid == 0) *reinterpret_cast<volatile uint32_t *>(sm.gmax + 3) = 0u; // the exchange loads are back: the producer may open its window
+    float inv0, inv1, inv2;
+    {   // scale of vector v (IEEE division: the same bits in every thread and every CTA)
+        const float m0 = __uint_as_float(sm.gmax[0]), m1 = __uint_as_float(sm.gmax[1]), m2 = __uint_as_float(sm.gmax[2]);
+        inv0 = m0 > 0.0f ? (float)kQMax / m0 : 0.0f;
+        inv1 = m1 > 0.0f ? (float)kQMax / m1 : 0.0f;
+        inv2 = m2 > 0.0f ? (float)kQMax / m2 : 0.0f;
+        if (ctid < 3) sm.scal[ctid] = (double)(ctid == 0 ? m0 : ctid == 1 ? m1 : m2) * (1.0 / (double)kQMax);
+    }
     const uint32_t pl0 = smem_u32(sm.planes);
 #pragma unroll
     for (int i = 0; i < kGatherMax; ++i) {
@@ -458,7 +448,30 @@ __device__ __forceinline__ void gather(const Params &p, const Smem &sm, const fl
             quantize4(f[i], iv, pl0 + (uint32_t)(4 * gg + 2 * v * N), (uint32_t)N);
         }
     }
+    {   // this warp's part of the offset sums (fixed trees), then warps 0..7 in order by thread v
+        double t0 = has_rec ? pair_to_double(ra[0], rb[0]) : 0.0, t1 = has_rec ? pair_to_double(ra[1], rb[1]) : 0.0,
+               t2 = has_rec ? pair_to_double(ra[2], rb[2]) : 0.0;
+        __syncwarp();
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            t0 += __shfl_xor_sync(0xffffffffu, t0, o);
+            t1 += __shfl_xor_sync(0xffffffffu, t1, o);
+            t2 += __shfl_xor_sync(0xffffffffu, t2, o);
+        }
+        if (lane == 0) {
+            sm.osum[wq * 3 + 0] = t0;
+            sm.osum[wq * 3 + 1] = t1;
+            sm.osum[wq * 3 + 2] = t2;
+        }
+    }
     tok_sync();
+    if (ctid < 3) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) t += sm.osum[w * 3 + ctid];
+        sm.scal[3 + ctid] = t;  // read by the epilogue, after the GEMV and its barrier
+        sm.gmax[ctid] = 0u;     // for the next gather
+    }
     trace_stamp(trace, sm.scal, ctid); // planes ready
 }
 
@@ -709,6 +722,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_token(const __grid_constant__ P
         *reinterpret_cast<int *>(sm.scal + 8) = 0;
         *reinterpret_cast<int *>(sm.scal + 9) = 0;
         for (int i = 0; i < 16; ++i) sm.clk[i] = 0;
+        for (int i = 0; i < 4; ++i) sm.gmax[i] = 0u;
     }
     unsigned long long *const c_trace = (TRACE && !(p.dbg & 4)) ? p.trace : nullptr;
     auto stamp = [&]() {
@@ -929,6 +943,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_token(const __grid_constant__ P
             }
         }
         tok_sync();
+        if (ctid == 0) *reinterpret_cast<volatile uint32_t *>(sm.gmax + 3) = 1u; // exchanges ahead: the producer narrows its window
         stamp();
         cp_async_wait();
         // -------- epilogue ----------------------------------------------------------------------------
