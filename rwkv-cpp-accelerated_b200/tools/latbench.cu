@@ -227,3 +227,103 @@ struct Part2 {
         }
     }
 } part2_runs_before_main_returns;
+
+// ---- part 3: the all-gather itself: every CTA reads the same `bytes` of exchanged data with `per` 16-byte strong loads
+// per thread (256 threads), all CTAs at the same moment; with and without bulk copies streaming in the background.
+__global__ void __launch_bounds__(384, 1) k_allgather(const unsigned char *src, const uint4 *vec, int groups, long long *out, int stream, int rotate) {
+    extern __shared__ __align__(128) unsigned char smem3[];
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem3 + 200000);
+    volatile int *stop = reinterpret_cast<volatile int *>(smem3 + 200064);
+    const int warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        *stop = 0;
+    }
+    __syncthreads();
+    if (warp >= 8) {
+        if (warp == 8 && (threadIdx.x & 31) == 0 && stream) {
+            uint32_t parity = 0;
+            size_t off = (size_t)blockIdx.x * 32768;
+            while (!*stop) {
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(32768 * stream) : "memory");
+                for (int k = 0; k < stream; ++k)
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(smem3 + 32768 * k)),
+                                 "l"(src + off + (size_t)k * 32768 * 148), "r"(32768), "r"(smem_addr(bar))
+                                 : "memory");
+                uint32_t ok = 0;
+                while (!ok) {
+                    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+                }
+                parity ^= 1;
+                off = (off + (size_t)32768 * 148 * stream) & ((1ull << 30) - 1);
+            }
+        }
+        return;
+    }
+    const int t = threadIdx.x;
+    long long t0 = clock64();
+    while (clock64() - t0 < 40000) {} // let the stream reach its steady state
+    long long best = 1ll << 60, sum = 0;
+    uint32_t acc = 0;
+    for (int rep = 0; rep < 8; ++rep) {
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const int rot = rotate ? (int)(((unsigned)groups * blockIdx.x) / gridDim.x) : 0;
+        const long long a = clock64();
+        uint4 f[20];
+#pragma unroll
+        for (int i = 0; i < 20; ++i) {
+            int g = t + 256 * i + rot;
+            if (g >= groups) g -= groups;
+            if (t + 256 * i < groups) asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(f[i].x), "=r"(f[i].y), "=r"(f[i].z), "=r"(f[i].w) : "l"(vec + g) : "memory");
+            else f[i] = make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int i = 0; i < 20; ++i) acc += f[i].x ^ f[i].w;
+        asm volatile("" ::"r"(acc) : "memory");
+        const long long b = clock64();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (b - a < best) best = b - a;
+        sum += b - a;
+        long long w0 = clock64();
+        while (clock64() - w0 < 6000) {} // the CTAs drift apart and meet again like the token kernel's phases
+    }
+    if (t == 0) {
+        out[2 * blockIdx.x] = sum / 8;
+        out[2 * blockIdx.x + 1] = best + (acc & 1);
+    }
+    *stop = 1;
+}
+
+struct Part3 {
+    Part3() {
+        unsigned char *src;
+        uint4 *vec;
+        long long *out, h[2 * 148];
+        cudaMalloc(&src, (1ull << 30) + (64 << 20));
+        cudaMalloc(&vec, 1 << 20);
+        cudaMalloc(&out, sizeof(h));
+        cudaMemset(vec, 0, 1 << 20);
+        cudaFuncSetAttribute(k_allgather, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+        for (int groups : {1024, 3072, 4096}) {
+            for (int stream : {0, 1, 3}) {
+                for (int rotate : {0, 1}) {
+                    k_allgather<<<148, 384, 232448>>>(src, vec, groups, out, stream, rotate);
+                    cudaError_t e = cudaDeviceSynchronize();
+                    if (e != cudaSuccess) {
+                        printf("allgather error: %s\n", cudaGetErrorString(e));
+                        return;
+                    }
+                    cudaMemcpy(h, out, sizeof(h), cudaMemcpyDeviceToHost);
+                    long long mean = 0, mx = 0;
+                    for (int b = 0; b < 148; ++b) {
+                        mean += h[2 * b];
+                        if (h[2 * b] > mx) mx = h[2 * b];
+                    }
+                    printf("all-gather of %5d x 16 B by 148 CTAs, %d tiles streaming per SM, rotate %d: mean %lld cycles, slowest CTA %lld\n", groups,
+                           stream, rotate, mean / 148, mx);
+                }
+            }
+        }
+    }
+} part3_runs_before_main_returns;
