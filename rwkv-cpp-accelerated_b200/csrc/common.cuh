@@ -75,6 +75,7 @@ struct Params {
     int greedy;             // 1: finish with an on-device argmax into ctrl->next
     int issue_gap;          // minimum SM cycles between two bulk-copy issues of the producer (0 = unpaced)
     int window;             // bulk copies in flight per CTA (<= stages)
+    int rotate;             // gather: every CTA starts at a different offset of the vector (experiment)
     int bwindow;            // bulk copies in flight per CTA while the consumers exchange vectors (latency of their loads)
     int pf_dist;            // tiles the L2 prefetch cursor runs ahead of the ring (0 = no L2 prefetch)
     int dbg;                // debug experiments (bit 0: run the slice statistics twice, cold / warm code)

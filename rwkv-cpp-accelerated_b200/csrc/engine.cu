@@ -786,6 +786,8 @@ int rwkv_b200_set_option(rwkv_b200_model *m, const char *key, const char *value)
     } else if (k == "window") {
         if (v < 1 || v > rk::kMaxStages) return fail(1, "window must be 1..%d", rk::kMaxStages);
         m->p.window = v;
+    } else if (k == "rotate") {
+        m->p.rotate = v != 0;
     } else if (k == "bwindow") {
         if (v < 1 || v > rk::kMaxStages) return fail(1, "bwindow must be 1..%d", rk::kMaxStages);
         m->p.bwindow = v;

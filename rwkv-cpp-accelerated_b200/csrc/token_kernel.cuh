@@ -340,7 +340,9 @@ __device__ __forceinline__ void gather(const Params &p, const Smem &sm, const fl
     const uint32_t tag2 = tag & 3u;
     const int ng = N >> 2;        // groups per vector
     const int total = nvec * ng;  // <= 256 * kGatherMax
-    const int base = ctid + (int)(((unsigned int)total * blockIdx.x) / gridDim.x);
+    // (starting every CTA at a different offset of the vector was measured slower than all CTAs walking it in the
+    // same order: tools/latbench.cu part 3, 2217 vs 2336 cycles for 48 KB; option "rotate" keeps the experiment)
+    const int base = ctid + (p.rotate ? (int)(((unsigned int)total * blockIdx.x) / gridDim.x) : 0);
     const int cnt = (total - ctid + kConsumers - 1) / kConsumers; // groups of this thread (may be <= 0)
     const uint4 *src = reinterpret_cast<const uint4 *>(vec);
     auto index = [&](int i) {
