@@ -654,11 +654,14 @@ __device__ __forceinline__ void publish_slice(const Smem &sm, TaggedDouble *recs
     }
 }
 
-// Sum over the G ranks of the partial result `part` of residual element j (a row-split GEMV): store
-// it into every peer's inbox, wait for the peers' parts, add in rank order (identical on every rank).
-__device__ __noinline__ double peer_sum(const Params &p, unsigned int off_in, int j, double part, uint32_t tag, unsigned int layer) {
-    for (int g = 0; g < p.G; ++g)
-        if (g != p.rank) st_tagged_double(xch_at<TaggedDouble>(p, g, off_in) + ((size_t)p.rank * p.E + j), part, tag, true);
+// Sum over the G ranks of the partial result `part` of residual element j (a row-split GEMV): store it into
+// every peer's inbox, wait for the peers' parts, add in rank order (identical on every rank). Called by whole
+// warps (`valid` = this lane owns an element); the polling loop is warp-uniform.
+__device__ __noinline__ double peer_sum(const Params &p, unsigned int off_in, int j, double part, bool valid, uint32_t tag,
+                                        unsigned int layer) {
+    if (valid)
+        for (int g = 0; g < p.G; ++g)
+            if (g != p.rank) st_tagged_double(xch_at<TaggedDouble>(p, g, off_in) + ((size_t)p.rank * p.E + j), part, tag, true);
     double tot = 0.0;
     const TaggedDouble *in = xch_at<TaggedDouble>(p, p.rank, off_in);
     Waiter w = waiter_begin();
@@ -667,10 +670,14 @@ __device__ __noinline__ double peer_sum(const Params &p, unsigned int off_in, in
             tot += part;
             continue;
         }
-        unsigned long long a, b;
+        unsigned long long a = tag64(0u, tag), b = a;
         for (;;) {
-            ld_pair(&in[(size_t)g * p.E + j], a, b, true);
-            if (tags_ok(a, b, tag)) break;
+            bool bad = false;
+            if (valid) {
+                ld_pair(&in[(size_t)g * p.E + j], a, b, true);
+                bad = !tags_ok(a, b, tag);
+            }
+            if (!__any_sync(0xffffffffu, bad)) break;
             if (waiter_tick(p, w)) wait_expired(p, kDiagPeerSum, layer, (unsigned int)g, tag, (unsigned int)(a >> 32), (unsigned long long)j);
         }
         tot += pair_to_double(a, b);
@@ -678,12 +685,18 @@ __device__ __noinline__ double peer_sum(const Params &p, unsigned int off_in, in
     return tot;
 }
 
-// sigmoid(ffn r) of residual element j, published by the owner of that channel (any rank)
-__device__ __noinline__ float peer_sr(const Params &p, int j, uint32_t tag, unsigned int layer) {
+// sigmoid(ffn r) of residual element j, published by the owner of that channel (any rank). Whole warps.
+__device__ __noinline__ float peer_sr(const Params &p, int j, bool valid, uint32_t tag, unsigned int layer) {
     const unsigned long long *srp = xch_at<unsigned long long>(p, p.rank, p.off_sr) + j;
-    unsigned long long a;
+    unsigned long long a = tag64(0u, tag);
     Waiter w = waiter_begin();
-    while ((uint32_t)((a = ld_word(srp, true)) >> 32) != tag) {
+    for (;;) {
+        bool bad = false;
+        if (valid) {
+            a = ld_word(srp, true);
+            bad = (uint32_t)(a >> 32) != tag;
+        }
+        if (!__any_sync(0xffffffffu, bad)) break;
         if (waiter_tick(p, w)) wait_expired(p, kDiagSr, layer, 0, tag, (unsigned int)(a >> 32), (unsigned long long)j);
     }
     return __uint_as_float((uint32_t)a);
@@ -983,9 +996,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_token(const __grid_constant__ P
         } else if (ph == 1) {
             // ======== residual (rwkv.cu:548-553), then LN2 + token shift (557-562) ========================
             if (owner_warps) {
+                double part = mine ? sm.scal[0] * row_total(0, ctid, 1) + sm.scal[3] : 0.0;
+                if (multi) part = peer_sum(p, p.off_in[0], j, part, mine, ep, (unsigned int)l);
                 if (mine) {
-                    double part = sm.scal[0] * row_total(0, ctid, 1) + sm.scal[3];
-                    if (multi) part = peer_sum(p, p.off_in[0], j, part, ep, (unsigned int)l);
                     const float y = (float)part;
                     const float xf = (float)sm.xown[ctid] + y; // the reference accumulates on an f32 copy of x
                     sm.xown[ctid] = (double)xf;
@@ -1040,15 +1053,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_token(const __grid_constant__ P
         } else if (ph == 3) {
             // ======== residual (rwkv.cu:574-577), then the next layer's LN1 (or LN_out) ====================
             if (owner_warps) {
+                double part = mine ? sm.scal[0] * row_total(0, ctid, 4) + sm.scal[3] : 0.0;
+                float sr = 0.0f;
+                if (multi) {
+                    part = peer_sum(p, p.off_in[1], j, part, mine, ep, (unsigned int)l);
+                    sr = peer_sr(p, j, mine, ep, (unsigned int)l);
+                } else if (mine) {
+                    sr = sm.srown[ctid];
+                }
                 if (mine) {
-                    double part = sm.scal[0] * row_total(0, ctid, 4) + sm.scal[3];
-                    float sr;
-                    if (multi) {
-                        part = peer_sum(p, p.off_in[1], j, part, ep, (unsigned int)l);
-                        sr = peer_sr(p, j, ep, (unsigned int)l);
-                    } else {
-                        sr = sm.srown[ctid];
-                    }
                     const float kv = (float)part;
                     sm.xown[ctid] = sm.xown[ctid] + (double)(kv * sr);
                 }
@@ -1103,11 +1116,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_token(const __grid_constant__ P
                     float b2 = -INFINITY;
                     int i2 = 0x7fffffff;
                     Waiter w = waiter_begin();
-                    for (int r = ctid; r < p.G * nb; r += kConsumers) {
-                        unsigned long long a, b;
+                    for (int r0 = 0; r0 < p.G * nb; r0 += kConsumers) {
+                        const int r = r0 + ctid;
+                        unsigned long long a = tag64(0xff800000u, p.tk), b = tag64(0x7fffffffu, p.tk); // (-inf, no index)
                         for (;;) {
-                            ld_pair(&cand[r], a, b, multi);
-                            if (tags_ok(a, b, p.tk)) break;
+                            bool bad = false;
+                            if (r < p.G * nb) {
+                                ld_pair(&cand[r], a, b, multi);
+                                bad = !tags_ok(a, b, p.tk);
+                            }
+                            if (!__any_sync(0xffffffffu, bad)) break;
                             if (waiter_tick(p, w)) wait_expired(p, kDiagArg, (unsigned int)l, 0, p.tk, (unsigned int)(a >> 32), (unsigned long long)r);
                         }
                         const float v = __uint_as_float((uint32_t)a);
@@ -1157,11 +1175,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_token(const __grid_constant__ P
             for (int g = 0; g < p.G; ++g)
                 st_word(xch_at<unsigned long long>(p, g, p.off_done) + ((size_t)p.rank * nb + blockIdx.x), tag64(1u, p.tk), true);
         }
-        if (ctid < p.G) {
-            const unsigned long long *d = xch_at<unsigned long long>(p, p.rank, p.off_done) + ((size_t)ctid * nb + blockIdx.x);
-            unsigned long long a;
+        if (ctid < 32) {
+            const unsigned long long *d = xch_at<unsigned long long>(p, p.rank, p.off_done) + ((size_t)(ctid < p.G ? ctid : 0) * nb + blockIdx.x);
+            unsigned long long a = 0;
             Waiter w = waiter_begin();
-            while ((uint32_t)((a = ld_word(d, true)) >> 32) != p.tk) {
+            for (;;) {
+                bool bad = false;
+                if (ctid < p.G) {
+                    a = ld_word(d, true);
+                    bad = (uint32_t)(a >> 32) != p.tk;
+                }
+                if (!__any_sync(0xffffffffu, bad)) break;
                 if (waiter_tick(p, w)) wait_expired(p, kDiagDone, (unsigned int)p.L_run, (unsigned int)ctid, p.tk, (unsigned int)(a >> 32), 0ull);
             }
             __threadfence_system();
