@@ -4,12 +4,13 @@
 Contract (driver): `python bench.py --gpus N --steps K --warmup W [--impl reference]`
 prints ONE JSON line on rank 0.
 
-  step      one decoded token (one pass of the hot path: 2 + 4*L kernels, + argmax)
-  workload  N=1: RWKV-4 7B shape (L=32, E=4096, uint8) — BASELINE.json's headline config —
-            random-init weights written by tools/genmodel.cpp in the reference's .bin format.
-            N>1: see --workload / DESIGN.md "multi-GPU".
-  value     tokens/s with everything resident in HBM: K graph replays back to back, each =
-            {feed previous argmax, forward, argmax}, CUDA events on the engine stream.
+  step      one decoded token = ONE launch of the persistent token kernel (embedding .. head, + arg-max)
+  workload  RWKV-4 7B shape (L=32, E=4096, uint8) — BASELINE.json's headline config — at every N (random-init
+            weights written by tools/genmodel.cpp in the reference's .bin format); --workload 14b for config 5.
+            N>1: ONE stream decoded by the N GPUs together (tensor parallel, strong scaling); N independent
+            replicas are measured as well and reported under `alt`.
+  value     tokens/s with everything resident in HBM: K launches back to back, each feeds the previous
+            arg-max on the device; CUDA events on the engine stream, max over ranks.
   e2e       tokens/s through the C-ABI call a user makes (rwkv_b200_forward with HOST token and
             HOST logits buffer: 32 B H2D + 201,108 B D2H + host argmax every step).
   roofline  dominant kernel class: algorithmic bytes per launch / mean CUDA-event duration of
@@ -183,8 +184,8 @@ def run_reference(args, pkg, workload):
 
 def ncu_traffic(kernel, workload):
     """DRAM bytes (read + write) per launch of the dominant kernel, from the committed `ncu --set full`
-    capture of the same command (profiles/r01f_token_traffic.json); null if there is none for this case."""
-    p = os.path.join(ROOT, "profiles", "r01f_token_traffic.json")
+    capture of the same command (profiles/r02_token_traffic.json); null if there is none for this case."""
+    p = os.path.join(ROOT, "profiles", "r02_token_traffic.json")
     try:
         with open(p) as f:
             t = json.load(f)
@@ -226,10 +227,11 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=None, choices=sorted(SHAPES))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--parallelism", default="replicas", choices=["tp", "replicas"],
-                    help="N > 1: which arrangement the headline `value` reports. 'replicas' = N independent streams, "
-                         "one per GPU (weak scaling, no data-path collective); 'tp' = ONE stream tensor-parallel over "
-                         "the N GPUs (strong scaling). The other arrangement is measured too and reported under `alt`.")
+    ap.add_argument("--parallelism", default="tp", choices=["tp", "replicas"],
+                    help="N > 1: which arrangement the headline `value` reports. 'tp' (default) = ONE stream decoded by the "
+                         "N GPUs together (strong scaling: column/row split of every matrix, two in-kernel NVLink exchanges "
+                         "per layer); 'replicas' = N independent streams, one per GPU (weak scaling, no exchange). The other "
+                         "arrangement is measured too and reported under `alt`.")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -339,8 +341,9 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         n_tok = args.steps * world if tp else args.steps
         alt = {"parallelism": ("replicas: %d independent streams, one per GPU (weak scaling)" % world) if tp
-               else ("tp%d: ONE stream over %d GPUs (strong scaling; rows of every matrix split over %d x 148 CTAs, peer "
-                     "stores + system-scope grid barrier over NVLink, no NCCL on the data path)" % (world, world, world))}
+               else ("tp%d: ONE stream over %d GPUs (strong scaling; K/V/R/ffn-K/ffn-R/head split by output channel, "
+                     "out-proj/ffn-V by input channel, two in-kernel NVLink exchanges of partial sums per layer, no NCCL "
+                     "on the data path)" % (world, world))}
         if float(ok.item()) > 0:
             alt.update({"value": round(n_tok / (float(t.item()) / 1e3), 2), "unit": "tokens/s",
                         "ms_per_token_per_stream": round(float(t.item()) / args.steps, 5)})
@@ -400,8 +403,10 @@ def main():
         "data": "synthetic",
         "config": {"workload": "RWKV-4 %s shape (L=%d, E=%d, V=50277) uint8, random-init reference-format .bin, greedy single-stream decode, batch 1" % (workload, L, E),
                    "l2": "inputs larger than L2: %.2f GB of weights per token vs 126 MB L2" % (abytes / 1e9),
-                   "parallelism": ("tp%d: one stream, rows of every matrix split over %d x 148 CTAs, peer stores + system-scope "
-                                   "grid barrier over NVLink, no NCCL on the data path" % (world, world)) if tp
+                   "parallelism": ("tp%d: one stream; K/V/R/ffn-K/ffn-R/head split by output channel, out-proj/ffn-V by input "
+                                   "channel, weights sharded at load, residual/layernorm replicated, two in-kernel exchanges of "
+                                   "partial sums per layer as self-tagged words stored into the peers over NVLink (no NCCL on the "
+                                   "data path)" % world) if tp
                    else ("replicas: 1 independent stream per GPU" if world > 1 else "1 GPU")},
         # per-GPU rate: tp -> each GPU streams 1/N of the bytes of every token; replicas -> 1/N of the tokens
         "hbm": {"algorithmic_bytes_per_token": abytes, "achieved_gbs": round(abytes * (value / world) / 1e9, 1),

@@ -1,20 +1,35 @@
 """Tensor-parallel plumbing: one process per GPU, `torch.distributed` only to swap the 64-byte CUDA IPC
-handles of the ranks' exchange blocks at start-up. The data path has no collective: the token kernel
-stores into the peers' blocks over NVLink and synchronises with a system-scope grid barrier
-(csrc/token_kernel.cuh)."""
+handles of the ranks' exchange blocks at start-up. The data path has no collective call: the token kernel
+stores its partial sums straight into the peers' exchange blocks over NVLink as self-tagged words
+(csrc/exchange.cuh) and every rank reads only its own memory.
+
+The split (csrc/common.cuh `Params`): rank g of G owns the att channels and ffn key channels
+[g*E/G, (g+1)*E/G) resp. [g*4E/G, (g+1)*4E/G): K, V, R, ffn-R and ffn-K are split by OUTPUT channel (columns of
+the file's [in][out] layout), out-proj and ffn-V by INPUT channel (rows), the head by vocabulary row; the
+loader reads only those slices. Residual stream, layernorm and token shift are replicated."""
 
 
-def partition(rows, grid, world):
-    """Row range [r0, r1) of every CTA of the grid formed by `world` ranks x `grid` CTAs - the same
-    arithmetic as split_rows_g() in csrc/token_kernel.cuh. Returns a list indexed by rank*grid + cta."""
-    n = grid * world
-    return [((rows * b) // n, (rows * (b + 1)) // n) for b in range(n)]
+def shard(n, world, rank):
+    """[lo, hi) of a dimension of size n owned by `rank` - the arithmetic of engine.cu (do_load)."""
+    return (n * rank) // world, (n * (rank + 1)) // world
 
 
-def rank_rows(rows, grid, world, rank):
-    """Rows [r0, r1) of a matrix that rank `rank` streams per token (union of its CTAs' ranges)."""
-    parts = partition(rows, grid, world)
-    return parts[rank * grid][0], parts[(rank + 1) * grid - 1][1]
+def cta_slices(n_embed, world, rank, grid=148, vocab=50277):
+    """Per-CTA row ranges inside rank `rank`'s shards - the arithmetic of make_slices() in csrc/token_kernel.cuh.
+    Returns four lists of (first, count): residual elements (global, identical on every rank), att channels,
+    ffn key channels and vocabulary rows (the last three relative to the rank's shard)."""
+    er = n_embed // world
+    v0, v1 = shard(vocab, world, rank)
+
+    def split(m):
+        return [((m * b) // grid, (m * (b + 1)) // grid - (m * b) // grid) for b in range(grid)]
+    return split(n_embed), split(er), split(4 * er), split(v1 - v0)
+
+
+def weight_bytes_per_rank(n_layers, n_embed, world, rank, vocab=50277):
+    """uint8 weight bytes rank `rank` streams per token: 13 L E^2 / G + its vocabulary rows."""
+    v0, v1 = shard(vocab, world, rank)
+    return 13 * n_layers * n_embed * (n_embed // world) + (v1 - v0) * n_embed
 
 
 def exchange_handles(handle, group=None):

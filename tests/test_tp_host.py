@@ -1,4 +1,4 @@
-"""Host side of the tensor-parallel path on CPU: the row partition over the grid formed by all ranks and
+"""Host side of the tensor-parallel path on CPU: the shard / slice arithmetic of the column-row split and
 the handle exchange over a world-size-2 gloo group (no GPU, no compute calls)."""
 import importlib
 import os
@@ -15,21 +15,30 @@ def tp():
     return importlib.import_module("rwkv-cpp-accelerated_b200").tp
 
 
-@pytest.mark.parametrize("rows", [768, 4096, 4 * 5120, 50277])
+@pytest.mark.parametrize("n_embed", [768, 2048, 4096, 5120])
 @pytest.mark.parametrize("world", [1, 2, 4, 8])
-def test_partition_covers_every_row_once(tp, rows, world):
-    grid = 148
-    parts = tp.partition(rows, grid, world)
-    assert len(parts) == grid * world
-    assert parts[0][0] == 0 and parts[-1][1] == rows
-    for (a0, a1), (b0, b1) in zip(parts, parts[1:]):
-        assert a1 == b0 and a0 <= a1            # contiguous, ascending, no overlap
-    sizes = [b - a for a, b in parts]
-    assert max(sizes) - min(sizes) <= 1         # balanced to one row
-    # a rank's CTAs own one contiguous block: that is what it streams from HBM per token
-    for r in range(world):
-        r0, r1 = tp.rank_rows(rows, grid, world, r)
-        assert r1 - r0 == sum(sizes[r * grid:(r + 1) * grid])
+def test_shards_and_slices_cover_everything_once(tp, n_embed, world):
+    """Every att channel, ffn key channel and vocabulary row belongs to exactly one (rank, CTA); the residual
+    slices are the same on every rank; the per-rank weight bytes add up to the whole model."""
+    grid, vocab, L = 148, 50277, 3
+    seen_c, seen_k, seen_v = [], [], []
+    for rank in range(world):
+        c0, c1 = tp.shard(n_embed, world, rank)
+        assert c1 - c0 == n_embed // world
+        k0, _ = tp.shard(4 * n_embed, world, rank)
+        v0, v1 = tp.shard(vocab, world, rank)
+        res, chan, keys, voc = tp.cta_slices(n_embed, world, rank, grid, vocab)
+        assert res == tp.cta_slices(n_embed, world, 0, grid, vocab)[0]
+        for lst, total in ((res, n_embed), (chan, n_embed // world), (keys, 4 * n_embed // world), (voc, v1 - v0)):
+            assert lst[0][0] == 0 and sum(n for _, n in lst) == total
+            assert all(a + n == b for (a, n), (b, _) in zip(lst, lst[1:]))   # contiguous, ascending
+            assert max(n for _, n in lst) - min(n for _, n in lst) <= 1      # balanced to one row
+        assert max(n for _, n in res) <= 64 and max(n for _, n in keys) <= 160  # kMaxSlice / kMaxKeys of the kernel
+        seen_c += [c0 + a + i for a, n in chan for i in range(n)]
+        seen_k += [k0 + a + i for a, n in keys for i in range(n)]
+        seen_v += [v0 + a + i for a, n in voc for i in range(n)]
+    assert seen_c == list(range(n_embed)) and seen_k == list(range(4 * n_embed)) and seen_v == list(range(vocab))
+    assert sum(tp.weight_bytes_per_rank(L, n_embed, world, r) for r in range(world)) == 13 * L * n_embed ** 2 + vocab * n_embed
 
 
 def _worker(rank, world, port, q):
