@@ -98,6 +98,7 @@ struct Params {
     const double *decay, *bonus;                       // [L][E]
     const double *expdecay;                            // [L][E] exp(decay), tabulated at load
     const float *emb;                                  // [V][E]
+    const double *ones;                                // [E] of 1.0 (batched prefill: "no token shift")
     double *sxy, *sdd;                                 // [slots][L][E] token-shift state (replicated)
     double *x;                                         // [E] residual stream after the last layer (tests)
     Ctrl *ctrl;

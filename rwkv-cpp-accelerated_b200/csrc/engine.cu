@@ -371,6 +371,14 @@ int do_load(M *m, const char *path, int quiet) {
         CK(cudaGetLastError());
         p.expdecay = ed;
     }
+    {
+        std::vector<double> one(E, 1.0);
+        double *d1 = nullptr;
+        if ((rc = dmalloc(m, &d1, (size_t)E))) return rc;
+        CK(cudaMemcpyAsync(d1, one.data(), E * sizeof(double), cudaMemcpyHostToDevice, m->stream));
+        CK(cudaStreamSynchronize(m->stream));
+        p.ones = d1;
+    }
     if ((rc = centre(m, kr, o1, L * E, &p.ock))) return rc;
     if ((rc = centre(m, vr, o2, L * E, &p.ocv))) return rc;
     if ((rc = centre(m, rr, o3, L * E, &p.ocr))) return rc;
