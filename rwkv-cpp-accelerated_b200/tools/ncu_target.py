@@ -1,4 +1,4 @@
-"""Short eager (no CUDA graph) decode for ncu: N tokens of the bench workload.
+"""Short decode for ncu (one launch of the token kernel per token): N tokens of the bench workload.
 usage: python ncu_target.py [workload=7b] [tokens=3]"""
 import importlib
 import os
@@ -12,7 +12,6 @@ pkg = importlib.import_module("rwkv-cpp-accelerated_b200")
 workload = sys.argv[1] if len(sys.argv) > 1 else "7b"
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 eng = pkg.Engine(bench.model_path(workload, pkg))
-eng.set_option("graph", 0)
 tok = bench.SEED_TOKEN
 for _ in range(n):
     tok = eng.forward_greedy(tok)

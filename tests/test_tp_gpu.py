@@ -18,9 +18,12 @@ def _gpus():
 
 
 @pytest.mark.parametrize("world,L,E,steps", [
-    (2, 2, 1024, 5),   # 148*2 CTAs over 1024 channels: 3-4 elements per CTA
+    (2, 2, 1024, 5),   # 512 channels per rank over 148 CTAs: 3-4 per CTA
     (2, 2, 4096, 4),   # 7B width
     (4, 1, 5120, 3),   # 14B width on four ranks
+    (4, 3, 768, 6),    # 169M width: 192 channels per rank, one or two per CTA
+    (8, 2, 4096, 3),   # 7B width on eight ranks: 512-byte row segments
+    (8, 1, 5120, 3),   # 14B width on eight ranks
 ])
 def test_tp_matches_oracle(pkg, make_model, tmp_path, world, L, E, steps):
     if _gpus() < world:
