@@ -54,13 +54,19 @@ int rwkv_b200_load(const char *path, unsigned long long max_gpt, int device, int
                    unsigned long long *n_embed);
 
 /* Tensor-parallel load: this process is rank `tp_rank` of `tp_size` (1..8) ranks,
- * one GPU each, that decode ONE stream together: the rows of
- * every matrix are split over the tp_size x 148 CTAs of all ranks; weights are
- * replicated, each rank streams only its rows. Every rank must then make the same
- * forward calls with the same tokens; all of them receive the same logits.
+ * one GPU each, that decode ONE stream together. Rank g owns the
+ * att channels [g*E/G, (g+1)*E/G) and the ffn key channels [g*4E/G, ...): K, V, R, ffn-R,
+ * ffn-K and the head are split by output channel, out-proj and ffn-V by input channel;
+ * the loader reads and keeps only this rank's slices (1/G of every matrix; n_embed must
+ * be a multiple of 16*G). The residual stream, layernorm and token shift are computed
+ * identically on every rank; two in-kernel exchanges of partial sums per layer cross
+ * NVLink. Every rank must make the same forward calls with the same tokens; all of them
+ * receive the same logits and hold the complete recurrent state afterwards (state_download
+ * works on any rank; state_upload must be given the same state on every rank).
  * `tp_size` = 1 is identical to rwkv_b200_load. After loading, wire the ranks with
- * rwkv_b200_tp_export / rwkv_b200_tp_import before the first forward.
- * No reference counterpart (the reference is single-GPU). */
+ * rwkv_b200_tp_export / rwkv_b200_tp_import before the first forward. A rank that stops
+ * calling makes the others fail with a time-out message (set_option "timeout_ms",
+ * default 60000) instead of hanging. No reference counterpart (the reference is single-GPU). */
 int rwkv_b200_load_tp(const char *path, unsigned long long max_gpt, int device, int quiet,
                       int tp_rank, int tp_size, rwkv_b200_model **out,
                       unsigned long long *n_layers, unsigned long long *n_embed);
@@ -102,7 +108,10 @@ int rwkv_b200_state_download(rwkv_b200_model *m, double *xy, double *aa, double 
 int rwkv_b200_state_zero(rwkv_b200_model *m);
 
 /* One forward over `n_tokens` tokens on the device-resident state; blocks until the
- * logits are in `logits_out` (host, n_tokens x 50277 floats).
+ * logits are in `logits_out` (host, n_tokens x 50277 floats). One token = one launch of
+ * the persistent token kernel; 16 tokens or more (one GPU) run as int8 tensor-core GEMMs
+ * over the whole chunk with the weights streamed once per 128 tokens - the same numbers
+ * (set_option "prefill" = "0" forces token by token).
  * Replaces `cuda_rwkv_parralel(...)` + the logits copy of `getOutput`
  * (R.h:104-122, R.cu:493-593, 471). mode GPT: tokens are consumed in order on state
  * slot 0; mode PARRALEL: token t uses state slot t. n_tokens <= max_gpt.
@@ -120,8 +129,8 @@ int rwkv_b200_forward_greedy(rwkv_b200_model *m, unsigned long long token,
  * it as `logits_out` avoids one host-side memcpy. This is what RWKV::out points at. */
 float *rwkv_b200_logits_host(rwkv_b200_model *m);
 
-/* Test hook: copy a named device vector ("x", "xs_o", "sr", "xs_v", "xy_new", "dd_new",
- * "logits") to `dst`. Returns the element count, or -1. */
+/* Test hook: copy a named device vector ("x" = residual stream after the last layer,
+ * "logits", "trace", "ptrace") to `dst`. Returns the element count, or -1. */
 long long rwkv_b200_debug_read(rwkv_b200_model *m, const char *name, void *dst, size_t dst_bytes);
 
 /* --- measurement hooks (bench.py); not part of the reference surface ------------ */
@@ -134,14 +143,14 @@ long long rwkv_b200_debug_read(rwkv_b200_model *m, const char *name, void *dst, 
 int rwkv_b200_decode_timed(rwkv_b200_model *m, const unsigned long long *tokens,
                            unsigned long long n, int teacher_forced, float *ms);
 
-/* Number of distinct kernels in one single-token forward, and their names. */
+/* Number of distinct kernels in one single-token forward (1: the token kernel), and their names. */
 int rwkv_b200_kernel_count(void);
 const char *rwkv_b200_kernel_name(int k);
 
-/* Run `n` single-token forwards launch-by-launch (no CUDA graph) with a CUDA-event
- * pair around every kernel launch; accumulates per-kernel-class totals.
+/* Run `n` single-token forwards with a CUDA-event pair around every launch.
  * ms_sum[k] = total ms spent in kernel class k, launches[k] = launch count,
- * bytes[k] = algorithmic HBM bytes of ONE launch of class k (weights + vectors). */
+ * bytes[k] = algorithmic HBM bytes of ONE launch of class k on this rank (its share of the
+ * weights + the vectors). */
 int rwkv_b200_profile(rwkv_b200_model *m, const unsigned long long *tokens,
                       unsigned long long n, float *ms_sum, unsigned long long *launches,
                       double *bytes);
@@ -159,14 +168,17 @@ unsigned long long rwkv_b200_launch_count(const rwkv_b200_model *m);
 int rwkv_b200_sample_typical(rwkv_b200_model *m, float temp, double u, unsigned long long *token,
                              double *margin);
 
-/* Engine knobs (all optional): key/value strings, e.g. ("graph","0"), ("pdl","1").
- * Returns non-zero for an unknown key. */
+/* Engine knobs (all optional), key/value strings: "window" / "bwindow" (bulk copies in
+ * flight per SM while streaming / while the CTAs exchange vectors), "pf_dist" (tiles the L2
+ * prefetch runs ahead), "stages" (ring depth), "poll_first", "rotate", "timeout_ms",
+ * "max_layers", "trace", "prefill". Returns non-zero for an unknown key. */
 int rwkv_b200_set_option(rwkv_b200_model *m, const char *key, const char *value);
 
 /* --- tensor-parallel wiring (tp_size > 1 only) --------------------------------- */
 
-/* Size in bytes of this rank's peer-visible exchange block (barrier counters,
- * accumulators, activation vectors, logits); allocated by the load. */
+/* Size in bytes of this rank's peer-visible exchange block (tagged activation vectors,
+ * per-CTA records, inboxes of the cross-GPU partial sums, logits, WKV state); allocated by
+ * the load. */
 size_t rwkv_b200_tp_buffer_bytes(const rwkv_b200_model *m);
 /* Export this rank's exchange buffer as a CUDA IPC handle (64 bytes). */
 int rwkv_b200_tp_export(rwkv_b200_model *m, void *ipc_handle_64);
