@@ -10,11 +10,15 @@ import bench  # noqa: E402
 
 pkg = importlib.import_module("rwkv-cpp-accelerated_b200")
 workload, steps = sys.argv[1], int(sys.argv[2])
-eng = pkg.Engine(bench.model_path(workload, pkg))
 L, E = bench.SHAPES[workload]
 ab = bench.algorithmic_bytes_per_token(L, E)
+DEFAULTS = {"window": 3, "bwindow": 1, "pf_dist": 4, "poll_first": 2, "rotate": 0, "issue_gap": 0}
+eng = pkg.Engine(bench.model_path(workload, pkg))
+stages0 = None
 for spec in sys.argv[3:]:
     try:
+        for k, v in DEFAULTS.items():  # every spec starts from the defaults
+            eng.set_option(k, v)
         for kv in spec.split(","):
             if kv:
                 k, v = kv.split("=")
