@@ -662,26 +662,31 @@ __device__ __noinline__ double peer_sum(const Params &p, unsigned int off_in, in
     if (valid)
         for (int g = 0; g < p.G; ++g)
             if (g != p.rank) st_tagged_double(xch_at<TaggedDouble>(p, g, off_in) + ((size_t)p.rank * p.E + j), part, tag, true);
-    double tot = 0.0;
     const TaggedDouble *in = xch_at<TaggedDouble>(p, p.rank, off_in);
-    Waiter w = waiter_begin();
-    for (int g = 0; g < p.G; ++g) {
-        if (g == p.rank) {
-            tot += part;
-            continue;
-        }
-        unsigned long long a = tag64(0u, tag), b = a;
-        for (;;) {
-            bool bad = false;
-            if (valid) {
-                ld_pair(&in[(size_t)g * p.E + j], a, b, true);
-                bad = !tags_ok(a, b, tag);
-            }
-            if (!__any_sync(0xffffffffu, bad)) break;
-            if (waiter_tick(p, w)) wait_expired(p, kDiagPeerSum, layer, (unsigned int)g, tag, (unsigned int)(a >> 32), (unsigned long long)j);
-        }
-        tot += pair_to_double(a, b);
+    const unsigned long long none = tag64(0u, tag);
+    unsigned long long a[kMaxRanks], b[kMaxRanks];
+#pragma unroll
+    for (int g = 0; g < kMaxRanks; ++g) { // all peers' words in flight at once
+        a[g] = b[g] = none;
+        if (valid && g < p.G && g != p.rank) ld_pair(&in[(size_t)g * p.E + j], a[g], b[g], true);
     }
+    Waiter w = waiter_begin();
+    for (;;) {
+        bool bad = false;
+#pragma unroll
+        for (int g = 0; g < kMaxRanks; ++g) {
+            if (!tags_ok(a[g], b[g], tag)) {
+                ld_pair(&in[(size_t)g * p.E + j], a[g], b[g], true);
+                bad = true;
+            }
+        }
+        if (!__any_sync(0xffffffffu, bad)) break;
+        if (waiter_tick(p, w)) wait_expired(p, kDiagPeerSum, layer, 0, tag, (unsigned int)(a[p.rank == 0 ? 1 : 0] >> 32), (unsigned long long)j);
+    }
+    double tot = 0.0;
+#pragma unroll
+    for (int g = 0; g < kMaxRanks; ++g) // rank order, the own part in its place: identical on every rank
+        if (g < p.G) tot += g == p.rank ? part : pair_to_double(a[g], b[g]);
     return tot;
 }
 
