@@ -147,35 +147,48 @@ __device__ __forceinline__ void produce_token(const Params &p, const Smem &sm, c
     pf = cp;
     bool pf_live = true;
     int tcount = 0, landed = 0, ahead = 0; // tiles issued; tiles known to have landed; lead of the prefetch cursor over the copy cursor
-    long long last_issue = 0;
+    const volatile uint32_t *const quiet_flag = reinterpret_cast<volatile uint32_t *>(sm.gmax + 3);
     TileRef t;
+    // The pending tile of the copy cursor. A non-blocking loop: top up the L2 prefetches, retire landed copies,
+    // issue the pending copy when a ring stage is free and the in-flight window allows it.
+    Waiter wt = waiter_begin();
     for (;;) {
-        while (pf_live && ahead < p.pf_dist + 1) { // keep L2 `pf_dist` tiles ahead of the ring
+        // While the consumers wait for exchanged words (`quiet`), everything this SM has in flight queues ahead of
+        // their loads (0.75 us per 32 KB tile) and every prefetch competes with them in L2: keep at most `bwindow`
+        // copies in flight and prefetch nothing. Epilogues, quantisation and the GEMV itself are not latency-bound:
+        // there the window is `window` copies and L2 is kept `pf_dist` tiles ahead, so HBM keeps streaming.
+        const bool quiet = *quiet_flag != 0u;
+        while (pf_live && (ahead < 1 || (!quiet && ahead < p.pf_dist + 1))) {
             TileRef q;
             pf_live = next_tile(p, sl, pf, q);
             if (!pf_live) break;
             if (p.pf_dist > 0 && ahead >= 1) // (the tile the copy cursor takes next is fetched by the copy itself)
-                // default L2 policy: with evict_first the stream of newer prefetches evicts the oldest ones - the tiles
-                // about to be consumed; the consuming copy then marks the lines evict_first
+                // default L2 policy: with evict_first the stream of newer prefetches would evict the oldest ones - the
+                // tiles about to be consumed; the consuming copy then marks the lines evict_first
                 asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(q.ptr), "r"(q.bytes) : "memory");
             ++ahead;
         }
         if (!next_tile(p, sl, cp, t)) break;
         --ahead;
-        // at most `window` copies in flight (`bwindow` while the consumers exchange vectors: everything this SM has
-        // in flight queues ahead of their loads, 0.75 us per 32 KB tile)
-        for (;;) {
-            const int win = *reinterpret_cast<volatile uint32_t *>(sm.gmax + 3) != 0u ? p.bwindow : p.window;
-            if (tcount - landed < win) break;
-            mbar_wait(p, full0 + 8 * wp.stage, wp.phase, kDiagRingFull);
-            wp.advance((uint32_t)p.stages);
-            ++landed;
-        }
-        // first pass over the ring: a fresh mbarrier reports the "previous" phase as complete
-        mbar_wait(p, empty0 + 8 * rp.stage, rp.phase ^ 1, kDiagRingEmpty);
-        if (p.issue_gap > 0) {
-            while (clock64() - last_issue < (long long)p.issue_gap) __nanosleep(32);
-            last_issue = clock64();
+        for (;;) { // until the pending tile is issued
+            while (landed < tcount && mbar_test_wait(full0 + 8 * wp.stage, wp.phase)) {
+                wp.advance((uint32_t)p.stages);
+                ++landed;
+            }
+            const int win = *quiet_flag != 0u ? p.bwindow : p.window;
+            // first pass over the ring: a fresh mbarrier reports the "previous" phase as complete
+            if (tcount - landed < win && mbar_test_wait(empty0 + 8 * rp.stage, rp.phase ^ 1)) break;
+            if (*quiet_flag == 0u && pf_live && ahead < p.pf_dist + 1) { // use the wait: prefetch further ahead
+                TileRef q;
+                pf_live = next_tile(p, sl, pf, q);
+                if (pf_live) {
+                    if (p.pf_dist > 0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(q.ptr), "r"(q.bytes) : "memory");
+                    ++ahead;
+                }
+            } else {
+                __nanosleep(40);
+            }
+            if (waiter_tick(p, wt)) wait_expired(p, kDiagRingEmpty, 0, 0, (unsigned int)tcount, (unsigned int)landed, 0ull);
         }
         const uint32_t fb = full0 + 8 * rp.stage;
         mbar_expect_tx(fb, t.bytes);
@@ -357,6 +370,7 @@ __device__ __forceinline__ void gather(const Params &p, const Smem &sm, const fl
     // poll_first 2: meet at the block barrier first - the owners of THIS CTA have published by then, and the
     // CTAs run in step, so one batch of loads normally finds everything (one L2 round trip, no polling
     // traffic while the owners still compute); 1: poll the first 16 bytes, then the batch; 0: batch at once.
+    if (ctid == 0) *reinterpret_cast<volatile uint32_t *>(sm.gmax + 3) = 1u; // latency-bound window: the producer goes quiet
     if (p.poll_first == 2) tok_sync();
     trace_stamp(trace, sm.scal, ctid); // G1: block met
     if (cnt > 0 && p.poll_first != 1) f[0] = ld_vec4(src + index(0));
@@ -490,14 +504,16 @@ __device__ __forceinline__ void gather(const Params &p, const Smem &sm, const fl
 struct StatsOut {
     double mean, rstd;
 };
-__device__ __noinline__ StatsOut slice_stats(const Params &p, const double *xown, double *scal, long long *clkp, TaggedDouble *recs, int ne,
-                                             uint32_t tag, unsigned int layer, int ctid, double c0, unsigned long long *trace) {
+__device__ __noinline__ StatsOut slice_stats(const Params &p, const double *xown, double *scal, long long *clkp, volatile uint32_t *quiet,
+                                             TaggedDouble *recs, int ne, uint32_t tag, unsigned int layer, int ctid, double c0,
+                                             unsigned long long *trace) {
     struct {
         const double *xown;
         double *scal;
         long long *clk;
     } sm{xown, scal, clkp};
     own_sync(); // xown complete
+    if (ctid == 0) *quiet = 1u; // latency-bound window: the producer goes quiet (token_kernel.cuh: produce_token)
     trace_stamp(trace, sm.scal, ctid); // S1: owners synchronised
     if (ctid < 32) {
         const int lane = ctid;
@@ -565,6 +581,7 @@ __device__ __noinline__ StatsOut slice_stats(const Params &p, const double *xown
             if (!__any_sync(0xffffffffu, bad)) break;
             if (waiter_tick(p, w)) wait_expired(p, kDiagStats, layer, 0, tag, (unsigned int)(a[0] >> 32), (unsigned long long)lane);
         }
+        if (ctid == 0) *quiet = 0u;
         trace_stamp(trace, sm.scal, ctid); // S4: every record here
         double st = 0.0, qt = 0.0;
 #pragma unroll
@@ -843,7 +860,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_token(const __grid_constant__ P
     // the last layer, LN_out -> publish the head input (rwkv.cu:585-588). Warps 0 and 1.
     auto slice_to_att = [&](int l) {
         const uint32_t ep = p.ep0 + 1u + (uint32_t)l;
-        const StatsOut so1 = slice_stats(p, sm.xown, sm.scal, sm.clk, stat0, ne, ep, (unsigned int)l, ctid, c0, c_trace);
+        const StatsOut so1 = slice_stats(p, sm.xown, sm.scal, sm.clk, reinterpret_cast<volatile uint32_t *>(sm.gmax + 3), stat0, ne, ep, (unsigned int)l, ctid, c0, c_trace);
         const double xmean = so1.mean, rstd = so1.rstd;
         c0 = xmean;
         stamp();
@@ -963,7 +980,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_token(const __grid_constant__ P
             }
         }
         tok_sync();
-        if (ctid == 0) *reinterpret_cast<volatile uint32_t *>(sm.gmax + 3) = 1u; // exchanges ahead: the producer narrows its window
         stamp();
         cp_async_wait();
         // -------- epilogue ----------------------------------------------------------------------------
@@ -1009,7 +1025,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_token(const __grid_constant__ P
                     sm.xown[ctid] = (double)xf;
                 }
                 stamp();
-                const StatsOut so2 = slice_stats(p, sm.xown, sm.scal, sm.clk, stat1, ne, ep, (unsigned int)l, ctid, c0, c_trace);
+                const StatsOut so2 = slice_stats(p, sm.xown, sm.scal, sm.clk, reinterpret_cast<volatile uint32_t *>(sm.gmax + 3), stat1, ne, ep, (unsigned int)l, ctid, c0, c_trace);
                 const double xmean = so2.mean, rstd = so2.rstd;
                 c0 = xmean;
                 stamp();
