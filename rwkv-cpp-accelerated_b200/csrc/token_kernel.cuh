@@ -157,8 +157,7 @@ __device__ __forceinline__ void produce_token(const Params &p, const Smem &sm, c
         // their loads (0.75 us per 32 KB tile) and every prefetch competes with them in L2: keep at most `bwindow`
         // copies in flight and prefetch nothing. Epilogues, quantisation and the GEMV itself are not latency-bound:
         // there the window is `window` copies and L2 is kept `pf_dist` tiles ahead, so HBM keeps streaming.
-        const bool quiet = *quiet_flag != 0u;
-        while (pf_live && (ahead < 1 || (!quiet && ahead < p.pf_dist + 1))) {
+        while (pf_live && ahead < 1) { // the prefetch cursor never falls behind the copy cursor
             TileRef q;
             pf_live = next_tile(p, sl, pf, q);
             if (!pf_live) break;
@@ -177,8 +176,12 @@ __device__ __forceinline__ void produce_token(const Params &p, const Smem &sm, c
             }
             const int win = *quiet_flag != 0u ? p.bwindow : p.window;
             // first pass over the ring: a fresh mbarrier reports the "previous" phase as complete
-            if (tcount - landed < win && mbar_test_wait(empty0 + 8 * rp.stage, rp.phase ^ 1)) break;
-            if (*quiet_flag == 0u && pf_live && ahead < p.pf_dist + 1) { // use the wait: prefetch further ahead
+            const bool slot_free = mbar_test_wait(empty0 + 8 * rp.stage, rp.phase ^ 1);
+            if (tcount - landed < win && slot_free) break;
+            // The ring is full (the consumers are in a boundary) and nobody waits for exchanged words: HBM would idle.
+            // Only then ask L2 for tiles further ahead - while the ring still takes copies, a prefetch of a far tile
+            // would only delay the near ones (same queue, same HBM).
+            if (!slot_free && *quiet_flag == 0u && pf_live && ahead < p.pf_dist + 1) {
                 TileRef q;
                 pf_live = next_tile(p, sl, pf, q);
                 if (pf_live) {
