@@ -621,7 +621,7 @@ int rwkv_b200_forward(rwkv_b200_model *m, const unsigned long long *tokens, unsi
     const size_t V = binfmt::kVocab;
     for (unsigned long long t = 0; t < n_tokens; ++t)
         if (tokens[t] >= V) return fail(1, "token id %llu out of range", tokens[t]);
-    if (n_tokens >= (unsigned long long)rk::kPrefillMinTokens && m->tp_size == 1 && rk::prefill_enabled(m->pf)) {
+    if (n_tokens >= (unsigned long long)m->pf.min_tokens && m->tp_size == 1 && rk::prefill_enabled(m->pf)) {
         rc = rk::prefill_forward(m->pf, m->p, m->stream, tokens, (int)n_tokens, mode == RWKV_B200_MODE_PARRALEL,
                                  logits_out ? m->h_logits : nullptr);
         if (rc) return fail(rc, "%s", rk::prefill_error());
@@ -818,6 +818,9 @@ int rwkv_b200_set_option(rwkv_b200_model *m, const char *key, const char *value)
         m->smem = smem;
     } else if (k == "prefill") {
         m->pf.disabled = v == 0;
+    } else if (k == "prefill_min") {
+        if (v < 2) return fail(1, "prefill_min must be >= 2");
+        m->pf.min_tokens = v;
     } else return fail(1, "unknown option '%s'", key);
     return 0;
 }

@@ -415,6 +415,7 @@ typedef CUresult (*PfnEncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_
 
 struct PrefillState {
     bool disabled = false;
+    int min_tokens = kPrefillMinTokens; // shorter calls run token by token through the decode kernel
     bool ready = false;
     int Tmax = 0;
     PfnEncodeTiled encode = nullptr;

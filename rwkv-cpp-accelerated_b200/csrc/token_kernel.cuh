@@ -103,8 +103,8 @@ __device__ __forceinline__ void load_sub(const Params &p, const Slices &sl, Tile
     case 1: c.N = E; c.tr = 8; c.nr = sl.nc; c.base = p.wv + mc + (size_t)sl.c0 * E; break;
     case 2: c.N = E; c.tr = 8; c.nr = sl.nc; c.base = p.wr + mc + (size_t)sl.c0 * E; break;
     case 3: c.N = Er; c.tr = 8; c.nr = sl.ne; c.base = p.wo + mc + (size_t)sl.e0 * Er; break;
-    case 4: c.N = E; c.tr = 8; c.nr = sl.nc; c.base = p.wfr + mc + (size_t)sl.c0 * E; break;
-    case 5: c.N = E; c.tr = 8; c.nr = sl.nk; c.base = p.wfk + 4 * mc + (size_t)sl.k0 * E; break;
+    case 4: c.N = E; c.tr = 8; c.nr = sl.nk; c.base = p.wfk + 4 * mc + (size_t)sl.k0 * E; break; // ffn K before ffn R
+    case 5: c.N = E; c.tr = 8; c.nr = sl.nc; c.base = p.wfr + mc + (size_t)sl.c0 * E; break;
     default: c.N = 4 * Er; c.tr = 2; c.nr = sl.ne; c.base = p.wfv + 4 * mc + (size_t)sl.e0 * 4 * Er; break;
     }
 }
@@ -915,28 +915,32 @@ __global__ void __launch_bounds__(kThreads, 1) k_token(const __grid_constant__ P
         slice_to_att(0);
     }
 
-    // ---- the phase loop: 4 phases per layer, then the head. One call site each for the gather and the
+    // ---- the phase loop: 5 phases per layer, then the head. One call site each for the gather and the
     // GEMV core keeps the layer body small enough for the instruction cache.
-    const int n_iter = 4 * p.L_run + 1;
+    // Phase 3 (ffn R) gathers nothing: its input was quantised together with ffn K's in phase 2 and its result
+    // (the sigmoid gate) is needed only after ffn V, so its 2.4 us of streaming run while the relu^2 keys of
+    // phase 2 travel to the other CTAs - phase 4's gather finds them in place.
+    const int n_iter = 5 * p.L_run + 1;
+    int l = 0, ph = 0;
     for (int it = 0; it < n_iter; ++it) {
-        const int itq = opaque(it);
-        const int l = itq >> 2;
-        const int ph = itq == 4 * p.L_run ? 4 : (itq & 3);
+        if (opaque(it) == 5 * p.L_run) ph = 5;
+        const int xi = ph < 3 ? ph : ph - 1; // index of the phase's exchange areas (kvr, o, rk, k4, head)
         const size_t lo = (size_t)l * E;
         const uint32_t ep = p.ep0 + 1u + (uint32_t)l;
         // -------- what this phase gathers and streams ---------------------------------------------
-        int nvec, N, nseg, nsub, nr0, nr1;
+        int nvec, N, nseg, nsub, nr0, sub0 = 0;
         uint32_t tag;
         switch (ph) {
-        case 0: nvec = 3; N = E; nseg = 1; nsub = 3; nr0 = nc; nr1 = nc; tag = ep; break;           // K, V, R
-        case 1: nvec = 1; N = Er; nseg = 1; nsub = 1; nr0 = ne; nr1 = 0; tag = ep; break;           // out-proj
-        case 2: nvec = 2; N = E; nseg = 1; nsub = 2; nr0 = nc; nr1 = nk; tag = ep; break;           // ffn R, ffn K
-        case 3: nvec = 1; N = 4 * Er; nseg = 4; nsub = 1; nr0 = ne; nr1 = 0; tag = ep; break;       // ffn V
-        default: nvec = 1; N = E; nseg = 1; nsub = 1; nr0 = sl.nv; nr1 = 0; tag = p.tk; break;      // head
+        case 0: nvec = 3; N = E; nseg = 1; nsub = 3; nr0 = nc; tag = ep; break;               // K, V, R
+        case 1: nvec = 1; N = Er; nseg = 1; nsub = 1; nr0 = ne; tag = ep; break;              // out-proj
+        case 2: nvec = 2; N = E; nseg = 1; nsub = 1; nr0 = nk; sub0 = 1; tag = ep; break;     // ffn K (input vector 1 of the gather)
+        case 3: nvec = 0; N = E; nseg = 1; nsub = 1; nr0 = nc; tag = ep; break;               // ffn R (input vector 0, already quantised)
+        case 4: nvec = 1; N = 4 * Er; nseg = 4; nsub = 1; nr0 = ne; tag = ep; break;          // ffn V
+        default: nvec = 1; N = E; nseg = 1; nsub = 1; nr0 = sl.nv; tag = p.tk; break;         // head
         }
-        const float *vec = reinterpret_cast<const float *>(xl + p.off_vec[ph]);
-        const TaggedDouble *offrec = reinterpret_cast<const TaggedDouble *>(xl + p.off_off[ph]);
-        const unsigned long long *maxrec = reinterpret_cast<const unsigned long long *>(xl + p.off_max[ph]);
+        const float *vec = reinterpret_cast<const float *>(xl + p.off_vec[xi]);
+        const TaggedDouble *offrec = reinterpret_cast<const TaggedDouble *>(xl + p.off_off[xi]);
+        const unsigned long long *maxrec = reinterpret_cast<const unsigned long long *>(xl + p.off_max[xi]);
         // -------- park the epilogue's parameters in shared memory ------------------------------------
         if (ph == 0) {
             if (owner_warps) { // WKV of channel cg (clamped: an idle thread reads a valid address)
@@ -966,20 +970,20 @@ __global__ void __launch_bounds__(kThreads, 1) k_token(const __grid_constant__ P
                 cp_async4(pk + 0, p.rfv + ko);
                 cp_async4(pk + 1, p.ocfv + ko);
             }
-        } else if (ph == 3) {
+        } else if (ph == 4) {
             if (owner_warps) fetch_ln1(l + 1);
         }
         // -------- gather + stream ------------------------------------------------------------------
-        gather(p, sm, vec, offrec, maxrec, nvec, N, tag, (unsigned int)l, ctid, c_trace);
+        if (nvec > 0) gather(p, sm, vec, offrec, maxrec, nvec, N, tag, (unsigned int)l, ctid, c_trace);
         {
             const bool exact = FULL && N == (nseg == 4 ? 4 * E : E); // segment == CPL * 512 bytes
-            uint32_t planes = c_planes, res = c_res;
+            // results: [sub][row]; ffn K's rows sit behind ffn R's (phase 3 fills those while phase 2's are read)
+            uint32_t planes = c_planes + (uint32_t)(sub0 * 3 * N), res = c_res + (uint32_t)(sub0 * nc) * 8u;
             for (int s = 0; s < nsub; ++s) {
-                const int nr = s == 0 ? nr0 : (ph == 0 ? nr0 : nr1);
-                if (exact) rp = consume_sub<CPL, false>(p, c_ring, c_full, c_empty, c_tile, c_stages, planes, res, N, nseg, nr, rp, c_warp, c_lane, c_ptrace, c_tcnt);
-                else rp = consume_sub<CPL, true>(p, c_ring, c_full, c_empty, c_tile, c_stages, planes, res, N, nseg, nr, rp, c_warp, c_lane, c_ptrace, c_tcnt);
+                if (exact) rp = consume_sub<CPL, false>(p, c_ring, c_full, c_empty, c_tile, c_stages, planes, res, N, nseg, nr0, rp, c_warp, c_lane, c_ptrace, c_tcnt);
+                else rp = consume_sub<CPL, true>(p, c_ring, c_full, c_empty, c_tile, c_stages, planes, res, N, nseg, nr0, rp, c_warp, c_lane, c_ptrace, c_tcnt);
                 planes += (uint32_t)(3 * N);
-                res += (uint32_t)(nr * nseg) * 8u;
+                res += (uint32_t)(nr0 * nseg) * 8u;
             }
         }
         tok_sync();
@@ -1053,14 +1057,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_token(const __grid_constant__ P
                 publish_slice<2>(sm, reinterpret_cast<TaggedDouble *>(xl + p.off_off[2]), reinterpret_cast<unsigned long long *>(xl + p.off_max[2]), of, mx, ep, ctid, ne);
             }
         } else if (ph == 2) {
-            // ======== sigmoid(ffn r) for the own channels, relu^2 of the own key channels (566-573) =======
-            if (minec) {
-                const float y = (float)(sm.scal[0] * row_total(0, ctid, 1) + sm.scal[3]);
-                const float sr = (float)(1.0 / (1.0 + exp(-(double)y)));
-                if (!multi) sm.srown[ctid] = sr; // one GPU: channel owner == residual owner
-                else
-                    for (int g = 0; g < p.G; ++g) st_word(xch_at<unsigned long long>(p, g, p.off_sr) + cg, tag64(__float_as_uint(sr), ep), true);
-            }
+            // ======== relu^2 of the own key channels (rwkv.cu:566-573) ====================================
             double of[1] = {0};
             uint32_t mx[1] = {0u};
             if (minek) {
@@ -1075,6 +1072,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_token(const __grid_constant__ P
             }
             publish_slice<1>(sm, reinterpret_cast<TaggedDouble *>(xl + p.off_off[3]), reinterpret_cast<unsigned long long *>(xl + p.off_max[3]), of, mx, ep, ctid, nk);
         } else if (ph == 3) {
+            // ======== sigmoid(ffn r) for the own channels ================================================
+            if (minec) {
+                const float y = (float)(sm.scal[0] * row_total(0, ctid, 1) + sm.scal[3]);
+                const float sr = (float)(1.0 / (1.0 + exp(-(double)y)));
+                if (!multi) sm.srown[ctid] = sr; // one GPU: channel owner == residual owner
+                else
+                    for (int g = 0; g < p.G; ++g) st_word(xch_at<unsigned long long>(p, g, p.off_sr) + cg, tag64(__float_as_uint(sr), ep), true);
+            }
+        } else if (ph == 4) {
             // ======== residual (rwkv.cu:574-577), then the next layer's LN1 (or LN_out) ====================
             if (owner_warps) {
                 double part = mine ? sm.scal[0] * row_total(0, ctid, 4) + sm.scal[3] : 0.0;
@@ -1187,6 +1193,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_token(const __grid_constant__ P
             }
         }
         stamp();
+        if (++ph == 5) {
+            ph = 0;
+            ++l;
+        }
     }
     if (multi) {
         // Everything this CTA stored into the peers (logits rows, WKV state) must have landed before any

@@ -39,7 +39,7 @@ GA = ["g.meet", "g.words", "g.max", "g.sync", "g.quant"]                    # ga
 names = ["ln0." + x for x in ST if not x.startswith("cold.")] + ["ln0.pub"]
 layer = ["kvr." + x for x in GA] + ["kvr.gemv", "kvr.epi"] + \
         ["out." + x for x in GA] + ["out.gemv", "out.resid"] + ["out." + x for x in ST] + ["out.ln2pub"] + \
-        ["rk." + x for x in GA] + ["rk.gemv", "rk.epi"] + \
+        ["rk." + x for x in GA] + ["rk.gemv", "rk.epi"] + ["fr.gemv", "fr.epi"] + \
         ["v." + x for x in GA] + ["v.gemv", "v.resid"] + ["v." + x for x in ST] + ["v.ln1pub", "v.end"]
 for _ in range(L):
     names += layer
@@ -58,7 +58,7 @@ for nm, lst in agg.items():
     tot += a.mean(0).sum()
     print("%-12s %8.2f %8.2f %8.2f %8.2f   x%d" % (nm, a.mean(), np.median(a), a.mean(1).min(), a.mean(1).max(), a.shape[1]))
     kind = ".".join(nm.split(".")[1:])
-    if nm.split(".")[0] in ("kvr", "out", "rk", "v"):
+    if nm.split(".")[0] in ("kvr", "out", "rk", "fr", "v"):
         groups[kind] = groups.get(kind, 0.0) + a.mean()
 print("sum of means (us):", round(tot, 1))
 print("per layer (us):", {k: round(v, 2) for k, v in groups.items()}, "total", round(sum(groups.values()), 2))
