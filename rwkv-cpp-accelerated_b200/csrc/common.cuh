@@ -53,7 +53,7 @@ struct Diag {
     unsigned long long aux;
 };
 constexpr unsigned int kDiagStats = 1, kDiagVec = 2, kDiagOff = 3, kDiagPeerSum = 4, kDiagSr = 5, kDiagDone = 6,
-                       kDiagArg = 7, kDiagRingFull = 8, kDiagRingEmpty = 9;
+                       kDiagArg = 7, kDiagRingFull = 8, kDiagRingEmpty = 9, kDiagPlanesFree = 10, kDiagPlanesReady = 11;
 
 // Everything the token kernel needs, passed by value (__grid_constant__).
 // G ranks (GPUs) decode ONE stream together (G = 1: a single GPU). Split:
@@ -75,7 +75,7 @@ struct Params {
     int greedy;             // 1: finish with an on-device argmax into ctrl->next
     int issue_gap;          // minimum SM cycles between two bulk-copy issues of the producer (0 = unpaced)
     int window;             // bulk copies in flight per CTA (<= stages)
-    int rotate;             // gather: every CTA starts at a different offset of the vector (experiment)
+    int cluster;            // CTAs per thread-block cluster (1, 2 or 4): they split the gather and write each other's limb planes
     int bwindow;            // bulk copies in flight per CTA while the consumers exchange vectors (latency of their loads)
     int pf_dist;            // tiles the L2 prefetch cursor runs ahead of the ring (0 = no L2 prefetch)
     int dbg;                // debug experiments (bit 0: run the slice statistics twice, cold / warm code)
@@ -149,6 +149,31 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
                  : "r"(bar), "r"(parity)
                  : "memory");
     return ok != 0;
+}
+// ---- thread-block cluster helpers (distributed shared memory) ---------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+// shared-window address `addr` of this CTA -> the same location in CTA `rank` of the cluster (shared::cluster window)
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+// 4-byte store into another CTA's shared memory that reports its bytes to an mbarrier of THAT CTA: whoever waits
+// for the barrier's phase sees the data - no fence on either side (a release at cluster scope costs microseconds
+// here: it drains everything the thread has in flight)
+__device__ __forceinline__ void st_async32(uint32_t remote_addr, uint32_t v, uint32_t remote_bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(remote_addr), "r"(v), "r"(remote_bar) : "memory");
+}
+// arrive on an mbarrier of another CTA of the cluster, no ordering implied
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t remote_bar) {
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() { // every thread of every CTA of the cluster
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 // non-blocking test of an mbarrier phase
 __device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
@@ -256,7 +281,7 @@ struct Smem {
     float *pf;           // [kMaxSlice][8]
     float *pk;           // [kMaxKeys][2]  ffn-V scale / offset of the own key channels
     long long *clk;      // [16] debug cycle counters (set_option dbg=4)
-    float *ginv;         // [4] 1 / S of the vectors of the current gather
+    uint64_t *cbar;      // [2] cluster mbarriers: [0] every CTA of the cluster has read its limb planes, [1] the planes are written
     uint32_t *gmax;      // [4] max |xs| of the vectors of the current gather (atomicMax of the warps' parts), [3] boundary flag
     double *osum;        // [kWarps][3] the warps' parts of the offset sums
 };
@@ -296,8 +321,8 @@ __device__ __forceinline__ Smem carve(uint8_t *base, const Params &p) {
     q += kWarps * 4 * sizeof(uint32_t);
     s.clk = reinterpret_cast<long long *>(q);
     q += 16 * sizeof(long long);
-    s.ginv = reinterpret_cast<float *>(q);
-    q += 4 * sizeof(float);
+    s.cbar = reinterpret_cast<uint64_t *>(q);
+    q += 2 * sizeof(uint64_t);
     s.gmax = reinterpret_cast<uint32_t *>(q);
     q += 4 * sizeof(uint32_t);
     s.osum = reinterpret_cast<double *>(q);

@@ -105,11 +105,12 @@ int sync_failed(M *m, cudaError_t e, const char *what) {
     const rk::Diag *d = m->h_diag;
     if (d && d->code) {
         static const char *names[] = {"", "slice statistics", "activation vector", "offset sums", "peer partial sums",
-                                      "sigmoid exchange", "completion flags", "arg-max candidates", "ring (full)", "ring (empty)"};
+                                      "sigmoid exchange", "completion flags", "arg-max candidates", "ring (full)", "ring (empty)",
+                                      "cluster: limb planes free", "cluster: limb planes written"};
         return fail(100 + (int)e,
                     "%s failed: %s; token kernel timed out waiting for %s: rank %u cta %u thread %u layer %u kind %u "
                     "expected tag %u saw %u aux %llu (a peer rank that never launched, or a protocol bug)",
-                    what, cudaGetErrorString(e), d->code < 10 ? names[d->code] : "?", d->rank, d->cta, d->thread, d->layer,
+                    what, cudaGetErrorString(e), d->code < 12 ? names[d->code] : "?", d->rank, d->cta, d->thread, d->layer,
                     d->kind, d->expect, d->seen, d->aux);
     }
     return fail(100 + (int)e, "%s failed: %s", what, cudaGetErrorString(e));
@@ -150,6 +151,21 @@ void configure_ring(M *m) {
     m->smem = rk::smem_bytes(p.stages, p.tile_bytes, p.plane_cap);
 }
 
+void fill_launch(int grid, int cluster, size_t smem, cudaLaunchConfig_t &cfg, cudaLaunchAttribute (&attrs)[2], cudaStream_t s) {
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(rk::kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    attrs[0].id = cudaLaunchAttributeCooperative;
+    attrs[0].val.cooperative = 1;
+    attrs[1].id = cudaLaunchAttributeClusterDimension;
+    attrs[1].val.clusterDim.x = (unsigned int)cluster;
+    attrs[1].val.clusterDim.y = 1;
+    attrs[1].val.clusterDim.z = 1;
+    cfg.attrs = attrs;
+    cfg.numAttrs = cluster > 1 ? 2 : 1;
+}
+
 int launch_token(M *m, int feed, bool greedy, const unsigned long long *stream, cudaStream_t s) {
     if (m->tp_size > 1 && !m->tp_wired)
         return fail(7, "tensor parallelism: call rwkv_b200_tp_import with every rank's handle before the first forward");
@@ -166,7 +182,12 @@ int launch_token(M *m, int feed, bool greedy, const unsigned long long *stream, 
     const bool full = m->E == (unsigned long long)m->cpl * 512ull;
     const void *fn = token_entry(m->cpl, full, m->p.trace != nullptr);
     if (!fn) return fail(3, "no kernel for %d chunks per lane", m->cpl);
-    CK(cudaLaunchCooperativeKernel(fn, dim3(m->grid), dim3(rk::kThreads), args, m->smem, s));
+    // cooperative: all CTAs resident together (they wait for each other's words); clusters of p.cluster CTAs share
+    // the gather through distributed shared memory
+    cudaLaunchConfig_t cfg{};
+    cudaLaunchAttribute attrs[2];
+    fill_launch(m->grid, m->p.cluster, m->smem, cfg, attrs, s);
+    CK(cudaLaunchKernelExC(&cfg, fn, args));
     m->launches += 1;
     return 0;
 }
@@ -275,6 +296,27 @@ bool grid_fits(unsigned long long E, unsigned long long Er, unsigned long long V
            3 * nc <= (unsigned long long)rk::kMaxRowsPerCta && nv <= (unsigned long long)rk::kMaxRowsPerCta;
 }
 
+// A grid of `grid` CTAs in clusters of `cluster`: divisibility, slice capacities, and - the CTAs wait for each
+// other's words - that the device can hold all of them at once.
+int check_grid(M *m, int grid, int cluster) {
+    if (cluster != 1 && cluster != 2 && cluster != 4) return fail(1, "cluster must be 1, 2 or 4");
+    if (grid < cluster || grid > m->sms || grid % cluster != 0)
+        return fail(1, "grid=%d must be a multiple of cluster=%d and at most %d (the SM count)", grid, cluster, m->sms);
+    if (!grid_fits(m->E, (unsigned long long)m->p.Er, (unsigned long long)m->p.Vr, grid))
+        return fail(5, "a grid of %d CTAs does not fit n_embed=%llu", grid, m->E);
+    if (cluster > 1) {
+        cudaLaunchConfig_t cfg{};
+        cudaLaunchAttribute attrs[2];
+        fill_launch(grid, cluster, m->smem, cfg, attrs, m->stream);
+        const bool full = m->E == (unsigned long long)m->cpl * 512ull;
+        int nclusters = 0;
+        CK(cudaOccupancyMaxActiveClusters(&nclusters, token_entry(m->cpl, full, m->p.trace != nullptr), &cfg));
+        if (nclusters * cluster < grid)
+            return fail(5, "the device holds %d clusters of %d CTAs at once; a grid of %d needs %d", nclusters, cluster, grid, grid / cluster);
+    }
+    return 0;
+}
+
 int do_load(M *m, const char *path, int quiet) {
     FileReader fr;
     fr.fd = open(path, O_RDONLY);
@@ -331,6 +373,7 @@ int do_load(M *m, const char *path, int quiet) {
     p.poll_first = 2;
     p.pf_dist = 4;
     p.bwindow = 1;
+    p.cluster = 1;
     if (p.stages < 2) return fail(5, "n_embed=%llu leaves no room for a two-stage ring", E);
     if (!grid_fits(E, Er, Vr, m->grid)) return fail(5, "a grid of %d CTAs does not fit n_embed=%llu", m->grid, E);
     const bool full = E == (unsigned long long)m->cpl * 512ull;
@@ -794,8 +837,11 @@ int rwkv_b200_set_option(rwkv_b200_model *m, const char *key, const char *value)
     } else if (k == "window") {
         if (v < 1 || v > rk::kMaxStages) return fail(1, "window must be 1..%d", rk::kMaxStages);
         m->p.window = v;
-    } else if (k == "rotate") {
-        m->p.rotate = v != 0;
+    } else if (k == "cluster" || k == "grid") {
+        const int c = k == "cluster" ? v : m->p.cluster, g = k == "grid" ? v : m->grid;
+        if (int rc2 = check_grid(m, g, c)) return rc2;
+        m->p.cluster = c;
+        m->grid = g;
     } else if (k == "bwindow") {
         if (v < 1 || v > rk::kMaxStages) return fail(1, "bwindow must be 1..%d", rk::kMaxStages);
         m->p.bwindow = v;

@@ -309,15 +309,16 @@ __device__ __forceinline__ uint32_t round_q(float xs, float inv) {
 __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
-// `plane0`: shared-window address of the element's word in limb plane 0; planes 1, 2 are `stride` bytes apart
-__device__ __forceinline__ void quantize4(const uint4 f, float inv, uint32_t plane0, uint32_t stride) {
+// four elements -> their word in each of the three limb planes
+struct PlaneWords {
+    uint32_t w0, w1, w2;
+};
+__device__ __forceinline__ PlaneWords quantize4(const uint4 f, float inv) {
     const uint32_t t0 = round_q(untag_f32(f.x), inv), t1 = round_q(untag_f32(f.y), inv);
     const uint32_t t2 = round_q(untag_f32(f.z), inv), t3 = round_q(untag_f32(f.w), inv);
     const uint32_t lo01 = __byte_perm(t0, t1, 0x5140), lo23 = __byte_perm(t2, t3, 0x5140);
     const uint32_t hi01 = __byte_perm(t0, t1, 0x0062), hi23 = __byte_perm(t2, t3, 0x0062);
-    sts32(plane0, __byte_perm(lo01, lo23, 0x5410));
-    sts32(plane0 + stride, __byte_perm(lo01, lo23, 0x7632));
-    sts32(plane0 + 2 * stride, __byte_perm(hi01, hi23, 0x5410));
+    return PlaneWords{__byte_perm(lo01, lo23, 0x5410), __byte_perm(lo01, lo23, 0x7632), __byte_perm(hi01, hi23, 0x5410)};
 }
 
 // ---- debug tracing --------------------------------------------------------------------------------------
@@ -352,20 +353,21 @@ __device__ __forceinline__ void trace_stamp(unsigned long long *trace, double *s
 constexpr int kGatherMax = 20; // 16-byte groups per thread: 256 x 20 x 4 >= 4 * 5120
 __device__ __forceinline__ void gather(const Params &p, const Smem &sm, const float *vec, const TaggedDouble *offrec,
                                        const unsigned long long *maxrec, int nvec,
-                                       int N, uint32_t tag, unsigned int layer, int ctid, unsigned long long *trace) {
+                                       int N, uint32_t tag, unsigned int layer, int ctid, int gk, unsigned long long *trace) {
     const uint32_t tag2 = tag & 3u;
     const int ng = N >> 2;        // groups per vector
     const int total = nvec * ng;  // <= 256 * kGatherMax
-    // (starting every CTA at a different offset of the vector was measured slower than all CTAs walking it in the
-    // same order: tools/latbench.cu part 3, 2217 vs 2336 cycles for 48 KB; option "rotate" keeps the experiment)
-    const int base = ctid + (p.rotate ? (int)(((unsigned int)total * blockIdx.x) / gridDim.x) : 0);
-    const int cnt = (total - ctid + kConsumers - 1) / kConsumers; // groups of this thread (may be <= 0)
+    // The C CTAs of a thread-block cluster split the gather: CTA r of the cluster fetches and quantises the r-th
+    // part of the concatenated vectors and writes the limb-plane words into the shared memory of all C CTAs
+    // (st.shared::cluster). All 148 SMs pulling the same 16..64 KB out of L2 is what bounds the exchange (L2
+    // bandwidth, tools/latbench.cu part 3) and the quantisation is ~2 us of ALU work per phase: both shrink by C.
+    // (Starting every CTA at a different offset of the vector was measured slower than walking it in the same order.)
+    const int C = p.cluster;
+    const int part = total / C;   // N is a multiple of 16: total is a multiple of 4
+    const int base = (C > 1 ? (int)cluster_ctarank() * part : 0) + ctid;
+    const int cnt = (part - ctid + kConsumers - 1) / kConsumers; // groups of this thread (may be <= 0)
     const uint4 *src = reinterpret_cast<const uint4 *>(vec);
-    auto index = [&](int i) {
-        int gg = base + kConsumers * i;
-        if (gg >= total) gg -= total;
-        return gg;
-    };
+    auto index = [&](int i) { return base + kConsumers * i; };
     const uint4 absent = make_uint4(tag2, tag2, tag2, tag2); // +0.0f carrying the tag: a slot this thread does not have
     uint4 f[kGatherMax];
     Waiter wt = waiter_begin();
@@ -447,6 +449,12 @@ __device__ __forceinline__ void gather(const Params &p, const Smem &sm, const fl
     trace_stamp(trace, sm.scal, ctid); // G3
     tok_sync(); // the maxima of all warps are in shared memory
     trace_stamp(trace, sm.scal, ctid); // G4
+    const bool probe = (p.dbg & 8) != 0; // cycle counters of the steps below, thread 0, summed over the token
+    long long pc[6];
+    auto tick = [&](int k) {
+        if (probe) asm volatile("mov.u64 %0, %%clock64;" : "=l"(pc[k])::"memory");
+    };
+    tick(0);
     if (ctid == 0) *reinterpret_cast<volatile uint32_t *>(sm.gmax + 3) = 0u; // the exchange loads are back: the producer may open its window
     float inv0, inv1, inv2;
     {   // scale of vector v (IEEE division: the same bits in every thread and every CTA)
@@ -457,16 +465,55 @@ __device__ __forceinline__ void gather(const Params &p, const Smem &sm, const fl
         if (ctid < 3) sm.scal[ctid] = (double)(ctid == 0 ? m0 : ctid == 1 ? m1 : m2) * (1.0 / (double)kQMax);
     }
     const uint32_t pl0 = smem_u32(sm.planes);
+    tick(1);
+    if (C == 1) {
 #pragma unroll
-    for (int i = 0; i < kGatherMax; ++i) {
-        if (i < cnt) {
-            // element 4*gg of the concatenated vectors sits 4*gg + v*2N bytes into the planes (3N bytes per vector)
-            const int gg = index(i);
-            const int v = (gg >= ng) + (gg >= 2 * ng);
-            const float iv = v == 0 ? inv0 : v == 1 ? inv1 : inv2;
-            quantize4(f[i], iv, pl0 + (uint32_t)(4 * gg + 2 * v * N), (uint32_t)N);
+        for (int i = 0; i < kGatherMax; ++i) {
+            if (i < cnt) {
+                // element 4*gg of the concatenated vectors sits 4*gg + v*2N bytes into the planes (3N bytes per vector)
+                const int gg = index(i);
+                const int v = (gg >= ng) + (gg >= 2 * ng);
+                const float iv = v == 0 ? inv0 : v == 1 ? inv1 : inv2;
+                const PlaneWords w = quantize4(f[i], iv);
+                const uint32_t a = pl0 + (uint32_t)(4 * gg + 2 * v * N);
+                sts32(a, w.w0);
+                sts32(a + (uint32_t)N, w.w1);
+                sts32(a + 2u * (uint32_t)N, w.w2);
+            }
+        }
+    } else {
+        // every CTA of the cluster has finished the GEMV that read its planes (signalled after that GEMV)
+        if (gk > 0) mbar_wait(p, smem_u32(sm.cbar), (uint32_t)(gk - 1) & 1u, kDiagPlanesFree);
+        const uint32_t me = cluster_ctarank(), bar1 = smem_u32(sm.cbar + 1);
+        uint32_t plr[4], barr[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            plr[r] = mapa(pl0, (uint32_t)(r < C ? r : 0));
+            barr[r] = mapa(bar1, (uint32_t)(r < C ? r : 0));
+        }
+#pragma unroll
+        for (int i = 0; i < kGatherMax; ++i) {
+            if (i < cnt) {
+                const int gg = index(i);
+                const int v = (gg >= ng) + (gg >= 2 * ng);
+                const float iv = v == 0 ? inv0 : v == 1 ? inv1 : inv2;
+                const PlaneWords w = quantize4(f[i], iv);
+                const uint32_t o = (uint32_t)(4 * gg + 2 * v * N);
+                sts32(pl0 + o, w.w0);
+                sts32(pl0 + o + (uint32_t)N, w.w1);
+                sts32(pl0 + o + 2u * (uint32_t)N, w.w2);
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    if (r < C && r != (int)me) {
+                        st_async32(plr[r] + o, w.w0, barr[r]);
+                        st_async32(plr[r] + o + (uint32_t)N, w.w1, barr[r]);
+                        st_async32(plr[r] + o + 2u * (uint32_t)N, w.w2, barr[r]);
+                    }
+                }
+            }
         }
     }
+    tick(2);
     {   // this warp's part of the offset sums (fixed trees), then warps 0..7 in order by thread v
         double t0 = has_rec ? pair_to_double(ra[0], rb[0]) : 0.0, t1 = has_rec ? pair_to_double(ra[1], rb[1]) : 0.0,
                t2 = has_rec ? pair_to_double(ra[2], rb[2]) : 0.0;
@@ -483,13 +530,32 @@ __device__ __forceinline__ void gather(const Params &p, const Smem &sm, const fl
             sm.osum[wq * 3 + 2] = t2;
         }
     }
-    tok_sync();
+    tick(3);
+    if (C == 1) {
+        tok_sync();
+    } else {
+        // "planes written": this CTA's eight warps arrive after their own stores; the other CTAs' words arrive as
+        // transaction bytes (12 per group of four elements) of their st.async
+        __syncwarp();
+        const uint32_t bar1 = smem_u32(sm.cbar + 1);
+        if (lane == 0) {
+            if (wq == 0) mbar_expect_tx(bar1, 12u * (uint32_t)(total - part));
+            else mbar_arrive(bar1);
+        }
+        mbar_wait(p, bar1, (uint32_t)gk & 1u, kDiagPlanesReady);
+    }
+    tick(4);
     if (ctid < 3) {
         double t = 0.0;
 #pragma unroll
         for (int w = 0; w < kWarps; ++w) t += sm.osum[w * 3 + ctid];
         sm.scal[3 + ctid] = t;  // read by the epilogue, after the GEMV and its barrier
         sm.gmax[ctid] = 0u;     // for the next gather
+    }
+    tick(5);
+    if (probe && ctid == 0) {
+        for (int k = 0; k < 5; ++k) sm.clk[8 + k] += pc[k + 1] - pc[k];
+        sm.clk[13] += 1;
     }
     trace_stamp(trace, sm.scal, ctid); // planes ready
 }
@@ -738,9 +804,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_token(const __grid_constant__ P
             mbar_init(smem_u32(&sm.full[i]), 1);
             mbar_init(smem_u32(&sm.empty[i]), kWarps);
         }
+        mbar_init(smem_u32(&sm.cbar[0]), (uint32_t)p.cluster);          // one arrival per CTA of the cluster
+        mbar_init(smem_u32(&sm.cbar[1]), (uint32_t)kWarps);    // the own consumer warps (+ the peers' st.async bytes)
         mbar_fence_init();
     }
     __syncthreads();
+    if (p.cluster > 1) cluster_sync_all(); // the peers' barriers exist before anybody arrives on them
     const int E = p.E, Er = p.Er;
     const int nb = (int)gridDim.x;
     const Slices sl = make_slices(E, Er, p.Vr, (int)blockIdx.x, nb);
@@ -921,7 +990,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_token(const __grid_constant__ P
     // (the sigmoid gate) is needed only after ffn V, so its 2.4 us of streaming run while the relu^2 keys of
     // phase 2 travel to the other CTAs - phase 4's gather finds them in place.
     const int n_iter = 5 * p.L_run + 1;
-    int l = 0, ph = 0;
+    int l = 0, ph = 0, gk = 0; // layer, phase, gathers so far
     for (int it = 0; it < n_iter; ++it) {
         if (opaque(it) == 5 * p.L_run) ph = 5;
         const int xi = ph < 3 ? ph : ph - 1; // index of the phase's exchange areas (kvr, o, rk, k4, head)
@@ -974,7 +1043,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_token(const __grid_constant__ P
             if (owner_warps) fetch_ln1(l + 1);
         }
         // -------- gather + stream ------------------------------------------------------------------
-        if (nvec > 0) gather(p, sm, vec, offrec, maxrec, nvec, N, tag, (unsigned int)l, ctid, c_trace);
+        if (nvec > 0) {
+            gather(p, sm, vec, offrec, maxrec, nvec, N, tag, (unsigned int)l, ctid, gk, c_trace);
+            ++gk;
+        }
         {
             const bool exact = FULL && N == (nseg == 4 ? 4 * E : E); // segment == CPL * 512 bytes
             // results: [sub][row]; ffn K's rows sit behind ffn R's (phase 3 fills those while phase 2's are read)
@@ -987,6 +1059,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_token(const __grid_constant__ P
             }
         }
         tok_sync();
+        // this CTA's limb planes may be overwritten - unless the next phase streams against them without a gather
+        // (2 -> 3); nobody gathers after the head
+        if (p.cluster > 1 && ctid == 0 && ph != 2 && ph != 5) {
+            const uint32_t bar = smem_u32(sm.cbar);
+            for (int r = 0; r < p.cluster; ++r) mbar_arrive_remote(mapa(bar, (uint32_t)r));
+        }
         stamp();
         cp_async_wait();
         // -------- epilogue ----------------------------------------------------------------------------

@@ -20,6 +20,15 @@ for i, nm in enumerate(["first trees", "publish+records", "syncwarp", "second tr
     per = tr[:, i] / n
     print("%-16s cycles per call: mean %.0f min %.0f max %.0f" % (nm, per.mean(), per.min(), per.max()))
 print("calls per token", n.mean())
+if int(os.environ.get("DBG", "4")) & 8:
+    tr = eng.read_trace().astype(np.int64)[:, :16]
+    n = tr[:, 13].clip(1)
+    for i, nm in enumerate(["scales (div)", "quantise loop", "offset trees", "barrier", "offset chain"]):
+        per = tr[:, 8 + i] / n
+        print("gather: %-16s cycles per call: mean %.0f min %.0f max %.0f" % (nm, per.mean(), per.min(), per.max()))
+    print("gathers per token", tr[:, 13].mean())
+    eng.close()
+    sys.exit(0)
 tr = eng.read_trace().astype(np.int64)[:, :16]
 n = tr[:, 12].clip(1)
 for i, nm in enumerate(["first trees", "publish+records", "syncwarp", "second trees"]):

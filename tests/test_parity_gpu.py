@@ -241,3 +241,30 @@ def test_oracle_vs_reference_cuda(pkg, make_model, tmp_path):
         if margin(ref) > 1e-3:
             assert int(got.argmax()) == int(ref.argmax())
     eng.close()
+
+
+@pytest.mark.parametrize("L,E", [(2, 256), (3, 768), (2, 2048), (2, 4096), (1, 5120)])
+def test_cluster_split_gather_is_bit_identical(pkg, make_model, L, E):
+    """Thread-block clusters split the gather / quantisation and write each other's limb planes through
+    distributed shared memory: the integers, hence the logits, must not change by a bit."""
+    path = make_model(L, E)
+    eng = make_engine(pkg, path)
+    toks = [SEED_TOKEN, 17, 40000, 5, 291, 1023]
+
+    def run():
+        eng.state_zero()
+        return np.stack([eng.forward([t])[0] for t in toks])
+
+    base = run()
+    tried = 0
+    for c in (2, 4):
+        try:
+            eng.set_option("cluster", c)
+        except pkg.EngineError as ex:  # the device cannot hold the grid in clusters of c
+            print("cluster=%d not available: %s" % (c, ex))
+            continue
+        tried += 1
+        got = run()
+        assert np.array_equal(got, base), "cluster=%d changed the logits" % c
+    eng.close()
+    assert tried >= 1
