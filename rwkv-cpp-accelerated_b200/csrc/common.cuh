@@ -263,6 +263,22 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+// Quantiser scale (decode kernel and batched path alike): 1 / m * kQMax without the IEEE division, whose range
+// check sends most calls into a ~100-instruction slow path here (ncu source view: 3 divisions = 870 cycles per
+// gather). Hardware reciprocal + one Newton step, then one multiplication - the same bits in every thread of every
+// CTA, and that is all the quantiser needs (the dequantisation scale m / kQMax is computed separately, in double).
+__device__ __forceinline__ float quant_scale(float m) {
+    if (!(m > 0.0f)) return 0.0f;
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(m));
+    r = fmaf(r, fmaf(-m, r, 1.0f), r);
+    float inv = (float)kQMax * r;
+    // |q| <= kQMax needs m * inv < kQMax + 0.5 exactly (the fma is exact to one rounding of a small number)
+    for (int k = 0; k < 3; ++k)
+        if (fmaf(m, inv, -(float)kQMax) >= 0.5f) inv = __uint_as_float(__float_as_uint(inv) - 1u);
+    return inv;
+}
+
 // ---------------------------------------------------------------------------------------
 // Shared-memory carve-up (dynamic shared memory, 128-byte aligned base)
 // ---------------------------------------------------------------------------------------

@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(256) k_pf_mix_quant(const __grid_constant__ Mi
         mx = pf_block_max(mx, shm);
         of = pf_block_sum(of, sh);
         const float mf = __uint_as_float(mx);
-        const float inv = mf > 0.0f ? (float)kQMax / mf : 0.0f;
+        const float inv = quant_scale(mf);
         if (threadIdx.x == 0) {
             a.scale[v * a.Tp + t] = (double)mf * (1.0 / (double)kQMax);
             a.offs[v * a.Tp + t] = of;
@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(256) k_pf_quant_rows(const float *xs, const fl
     mx = pf_block_max(mx, shm);
     of = pf_block_sum(of, sh);
     const float mf = __uint_as_float(mx);
-    const float inv = mf > 0.0f ? (float)kQMax / mf : 0.0f;
+    const float inv = quant_scale(mf);
     if (threadIdx.x == 0) {
         scale[t] = (double)mf * (1.0 / (double)kQMax);
         offs[t] = of;

@@ -457,11 +457,11 @@ __device__ __forceinline__ void gather(const Params &p, const Smem &sm, const fl
     tick(0);
     if (ctid == 0) *reinterpret_cast<volatile uint32_t *>(sm.gmax + 3) = 0u; // the exchange loads are back: the producer may open its window
     float inv0, inv1, inv2;
-    {   // scale of vector v (IEEE division: the same bits in every thread and every CTA)
+    {   // scale of vector v (the same bits in every thread and every CTA)
         const float m0 = __uint_as_float(sm.gmax[0]), m1 = __uint_as_float(sm.gmax[1]), m2 = __uint_as_float(sm.gmax[2]);
-        inv0 = m0 > 0.0f ? (float)kQMax / m0 : 0.0f;
-        inv1 = m1 > 0.0f ? (float)kQMax / m1 : 0.0f;
-        inv2 = m2 > 0.0f ? (float)kQMax / m2 : 0.0f;
+        inv0 = quant_scale(m0);
+        inv1 = quant_scale(m1);
+        inv2 = quant_scale(m2);
         if (ctid < 3) sm.scal[ctid] = (double)(ctid == 0 ? m0 : ctid == 1 ? m1 : m2) * (1.0 / (double)kQMax);
     }
     const uint32_t pl0 = smem_u32(sm.planes);

@@ -26,6 +26,7 @@ if int(os.environ.get("DBG", "4")) & 8:
     for i, nm in enumerate(["scales (div)", "quantise loop", "offset trees", "barrier", "offset chain"]):
         per = tr[:, 8 + i] / n
         print("gather: %-16s cycles per call: mean %.0f min %.0f max %.0f" % (nm, per.mean(), per.min(), per.max()))
+    print("active lanes with thread 0: after the barrier %.2f, after the quantise loop %.2f" % ((tr[:, 14] / n).mean(), (tr[:, 15] / n).mean()))
     print("gathers per token", tr[:, 13].mean())
     eng.close()
     sys.exit(0)

@@ -65,6 +65,9 @@ print("per layer (us):", {k: round(v, 2) for k, v in groups.items()}, "total", r
 
 # ---- tile-level: how far ahead of the consumers does the producer run? -------------------------
 tt = eng.read_tile_trace().astype(np.int64)
+if os.path.isdir(out_dir):
+    np.save(os.path.join(out_dir, "tile_raw_%s%s.npy" % (workload, os.environ.get("TRACE_TAG", ""))), (tt[:, :8] - t0).astype(np.int32))
+    np.save(os.path.join(out_dir, "trace_raw_%s%s.npy" % (workload, os.environ.get("TRACE_TAG", ""))), tr[:8].astype(np.int32))
 for cta in (0, 77):
     issue, ready = tt[0, cta], tt[1, cta]
     n_t = int((issue > 0).sum())
