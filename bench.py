@@ -390,6 +390,14 @@ def main():
                 "frac": round(kernels[dom]["gbs"] / peak, 4), "traffic": ncu_traffic(dom, workload) if world == 1 else None, "peak_source": peak_src,
                 "how": "algorithmic bytes per launch / mean CUDA-event duration per launch (eager profile run, %d tokens)" % len(prof_tokens)}
     abytes = algorithmic_bytes_per_token(L, E)
+    if world > 1:
+        # Launch-by-launch timing does not work across ranks (the peers' kernels of one token are not launched at the
+        # same instant, so an eagerly timed launch mostly waits for them): take the timed decode itself - one launch
+        # per token per GPU, CUDA events around the whole run, max over ranks - and the bytes ONE GPU streams per token.
+        per_gpu = abytes * (value / world) / 1e9
+        roofline.update({"achieved": round(per_gpu, 1), "frac": round(per_gpu / peak, 4),
+                         "how": "algorithmic bytes one GPU streams per launch (%s) / (device-timed decode / launches), max over ranks"
+                                % ("1/%d of a token's weights" % world if tp else "one token")})
     cb = None
     if not args.no_cpu_baseline and world == 1:
         cb = cpu_baseline(path, prof_tokens)

@@ -109,9 +109,10 @@ int rwkv_b200_state_zero(rwkv_b200_model *m);
 
 /* One forward over `n_tokens` tokens on the device-resident state; blocks until the
  * logits are in `logits_out` (host, n_tokens x 50277 floats). One token = one launch of
- * the persistent token kernel; 16 tokens or more (one GPU) run as int8 tensor-core GEMMs
- * over the whole chunk with the weights streamed once per 128 tokens - the same numbers
- * (set_option "prefill" = "0" forces token by token).
+ * the persistent token kernel; 8 tokens or more (one GPU; "prefill_min") run as int8
+ * tensor-core GEMMs over the whole chunk with the weights streamed once per 128 tokens -
+ * the same numbers; the chunk's launches are replayed as a CUDA graph per shape
+ * (set_option "prefill" = "0" forces token by token, "prefill_graph" = "0" eager launches).
  * Replaces `cuda_rwkv_parralel(...)` + the logits copy of `getOutput`
  * (R.h:104-122, R.cu:493-593, 471). mode GPT: tokens are consumed in order on state
  * slot 0; mode PARRALEL: token t uses state slot t. n_tokens <= max_gpt.
@@ -170,8 +171,10 @@ int rwkv_b200_sample_typical(rwkv_b200_model *m, float temp, double u, unsigned 
 
 /* Engine knobs (all optional), key/value strings: "window" / "bwindow" (bulk copies in
  * flight per SM while streaming / while the CTAs exchange vectors), "pf_dist" (tiles the L2
- * prefetch runs ahead), "stages" (ring depth), "poll_first", "rotate", "timeout_ms",
- * "max_layers", "trace", "prefill". Returns non-zero for an unknown key. */
+ * prefetch runs ahead), "stages" (ring depth), "poll_first", "timeout_ms", "max_layers",
+ * "trace", "prefill", "prefill_min", "prefill_graph", "grid" (CTAs, at most the SM count),
+ * "cluster" (1, 2 or 4 CTAs share a gather through distributed shared memory; measured
+ * without gain, default 1). Returns non-zero for an unknown key. */
 int rwkv_b200_set_option(rwkv_b200_model *m, const char *key, const char *value);
 
 /* --- tensor-parallel wiring (tp_size > 1 only) --------------------------------- */

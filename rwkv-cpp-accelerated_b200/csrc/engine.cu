@@ -864,6 +864,8 @@ int rwkv_b200_set_option(rwkv_b200_model *m, const char *key, const char *value)
         m->smem = smem;
     } else if (k == "prefill") {
         m->pf.disabled = v == 0;
+    } else if (k == "prefill_graph") {
+        m->pf.use_graph = v != 0;
     } else if (k == "prefill_min") {
         if (v < 2) return fail(1, "prefill_min must be >= 2");
         m->pf.min_tokens = v;

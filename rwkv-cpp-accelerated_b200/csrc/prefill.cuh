@@ -19,12 +19,13 @@
 #include <cuda.h>
 
 #include <string>
+#include <vector>
 
 #include "common.cuh"
 
 namespace rk {
 
-constexpr int kPrefillMinTokens = 16;  // shorter chunks run token by token through the decode kernel
+constexpr int kPrefillMinTokens = 8;   // shorter calls run token by token through the decode kernel (7B: break-even near 6)
 constexpr int kPfMaxTokens = 128;      // tokens per pass: the unsigned planes are N = 2 Tp <= 256 MMA columns
 constexpr int kPfBM = 128, kPfBK = 128, kPfStages = 3;
 constexpr int kPfThreads = 192;
@@ -426,6 +427,16 @@ struct PrefillState {
     float *rw = nullptr, *xs = nullptr, *sr = nullptr, *act = nullptr, *logits = nullptr;
     unsigned long long launches = 0;
     std::string err;
+    // One chunk is ~21 small launches per layer: replayed as a CUDA graph per (tokens, mode, logits) shape, so that a
+    // caller stepping T streams (MODE::PARRALEL) or prefilling in equal chunks pays the host side once.
+    struct Graph {
+        int T;
+        bool parallel, logits;
+        cudaGraphExec_t exec;
+        unsigned long long launches;
+    };
+    std::vector<Graph> graphs;
+    bool use_graph = true;
 };
 inline std::string &prefill_err_slot() {
     static thread_local std::string e;
@@ -439,6 +450,8 @@ inline unsigned long long prefill_launches(PrefillState &s) {
     return n;
 }
 inline void prefill_free(PrefillState &s) {
+    for (auto &g : s.graphs) cudaGraphExecDestroy(g.exec);
+    s.graphs.clear();
     for (void *p : {(void *)s.d_tokens, (void *)s.x, (void *)s.ln, (void *)s.scale, (void *)s.offs, (void *)s.limbs, (void *)s.C, (void *)s.rw, (void *)s.xs,
                     (void *)s.sr, (void *)s.act, (void *)s.logits})
         if (p) cudaFree(p);
@@ -522,14 +535,13 @@ inline int pf_gemm(PrefillState &s, cudaStream_t st, const int8_t *W, int M, int
 
 // One chunk of T <= 128 tokens on a single GPU. GPT: tokens in order on slot 0; PARRALEL: token t on slot t.
 // Per-token logits go to h_logits (pinned, [T][V]) if not null.
-inline int prefill_chunk(PrefillState &s, const Params &p, cudaStream_t st, const unsigned long long *tokens, int T, bool parallel, float *h_logits) {
+inline int prefill_chunk_body(PrefillState &s, const Params &p, cudaStream_t st, int T, bool parallel, bool want_logits) {
     const int E = p.E, L = p.L, Tp = (T + 15) & ~15;
     const size_t LE = (size_t)L * E;
     double *saa = reinterpret_cast<double *>(p.xch[p.rank] + p.off_saa), *sbb = reinterpret_cast<double *>(p.xch[p.rank] + p.off_sbb);
     const unsigned gT = (unsigned)T;
     auto blocks = [](size_t n) { return (unsigned)((n + 255) / 256); };
     int rc;
-    PF_CK(cudaMemcpyAsync(s.d_tokens, tokens, (size_t)T * 8, cudaMemcpyHostToDevice, st));
     PF_CK(cudaMemsetAsync(s.limbs, 0, (size_t)9 * Tp * 4 * E, st)); // padded token rows stay zero
     k_pf_embed<<<gT, 256, 0, st>>>(p.emb, p.ln, s.d_tokens, E, s.x);
     int *Ca = s.C, *Cb = s.C + (size_t)E * 3 * Tp, *Cc = s.C + (size_t)2 * E * 3 * Tp; // three accumulator sets; the big ones reuse [0]
@@ -588,7 +600,7 @@ inline int prefill_chunk(PrefillState &s, const Params &p, cudaStream_t st, cons
         s.launches += 10;
     }
     // ---- head -----------------------------------------------------------------------------------------------------
-    if (h_logits) {
+    if (want_logits) {
         k_pf_ln<<<gT, 256, 0, st>>>(s.x, p.ln + (size_t)(4 * L + 2) * E, p.ln + (size_t)(4 * L + 3) * E, E, s.ln);
         MixArgs h{}; // scale + quantise without a token shift: a mix vector of ones selects the current token only
         h.ln = s.ln;
@@ -602,10 +614,51 @@ inline int prefill_chunk(PrefillState &s, const Params &p, cudaStream_t st, cons
         k_pf_mix_quant<<<gT, 256, 0, st>>>(h);
         if ((rc = pf_gemm(s, st, p.whead, p.Vr, E, s.limbs, (size_t)3 * Tp, 0, Tp, s.C))) return rc;
         k_pf_logits<<<blocks((size_t)T * kVocab), 256, 0, st>>>(s.C, s.scale, s.offs, kVocab, T, Tp, s.logits);
-        PF_CK(cudaMemcpyAsync(h_logits, s.logits, (size_t)T * kVocab * 4, cudaMemcpyDeviceToHost, st));
         s.launches += 4;
     }
     PF_CK(cudaGetLastError());
+    return 0;
+}
+
+inline int prefill_chunk(PrefillState &s, const Params &p, cudaStream_t st, const unsigned long long *tokens, int T, bool parallel, float *h_logits) {
+    const bool want_logits = h_logits != nullptr;
+    int rc;
+    PF_CK(cudaMemcpyAsync(s.d_tokens, tokens, (size_t)T * 8, cudaMemcpyHostToDevice, st));
+    PrefillState::Graph *g = nullptr;
+    for (auto &e : s.graphs)
+        if (e.T == T && e.parallel == parallel && e.logits == want_logits) g = &e;
+    if (!g && s.use_graph) {
+        // record the chunk once (nothing runs during the capture), then replay it
+        const unsigned long long before = s.launches;
+        PF_CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        rc = prefill_chunk_body(s, p, st, T, parallel, want_logits);
+        cudaGraph_t graph = nullptr;
+        const cudaError_t ee = cudaStreamEndCapture(st, &graph);
+        const unsigned long long n = s.launches - before;
+        s.launches = before;
+        if (rc) {
+            if (graph) cudaGraphDestroy(graph);
+            return rc;
+        }
+        if (ee != cudaSuccess) return pf_fail("cudaStreamEndCapture", ee);
+        cudaGraphExec_t exec = nullptr;
+        const cudaError_t ei = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ei != cudaSuccess) return pf_fail("cudaGraphInstantiate", ei);
+        if (s.graphs.size() >= 8) {
+            cudaGraphExecDestroy(s.graphs.front().exec);
+            s.graphs.erase(s.graphs.begin());
+        }
+        s.graphs.push_back(PrefillState::Graph{T, parallel, want_logits, exec, n});
+        g = &s.graphs.back();
+    }
+    if (g) {
+        PF_CK(cudaGraphLaunch(g->exec, st));
+        s.launches += g->launches;
+    } else if ((rc = prefill_chunk_body(s, p, st, T, parallel, want_logits))) {
+        return rc;
+    }
+    if (want_logits) PF_CK(cudaMemcpyAsync(h_logits, s.logits, (size_t)T * kVocab * 4, cudaMemcpyDeviceToHost, st));
     return 0;
 }
 

@@ -20,11 +20,12 @@ eng.set_option("prefill_min", 2)
 rng = np.random.default_rng(1)
 
 
-def run(T, batched, mode):
+def run(T, batched, mode, graph=1):
     eng.set_option("prefill", 1 if batched else 0)
+    eng.set_option("prefill_graph", graph)
     toks = rng.integers(0, 50000, T)
     best = 1e9
-    for _ in range(3):
+    for _ in range(4):  # (the first batched call of a shape records its CUDA graph)
         eng.state_zero()
         t0 = time.perf_counter()
         eng.forward(toks, mode=mode, want_logits=False)
@@ -32,11 +33,11 @@ def run(T, batched, mode):
     return best * 1e3
 
 
-print("%-6s %-9s %12s %12s %9s %14s" % ("T", "mode", "batched ms", "by-token ms", "ratio", "batched tok/s"))
+print("%-6s %-9s %12s %12s %12s %9s %14s" % ("T", "mode", "batched ms", "no-graph ms", "by-token ms", "ratio", "batched tok/s"))
 for mode, name in ((1, "GPT"), (0, "PARRALEL")):
     for T in Ts:
         if mode == 0 and T > eng.max_gpt:
             continue
-        a, b = run(T, True, mode), run(T, False, mode)
-        print("%-6d %-9s %12.3f %12.3f %9.2f %14.0f" % (T, name, a, b, b / a, T / a * 1e3), flush=True)
+        a, a0, b = run(T, True, mode), run(T, True, mode, graph=0), run(T, False, mode)
+        print("%-6d %-9s %12.3f %12.3f %12.3f %9.2f %14.0f" % (T, name, a, a0, b, b / a, T / a * 1e3), flush=True)
 eng.close()
