@@ -255,6 +255,12 @@ __device__ __forceinline__ RingPos consume_sub(const Params &p, uint32_t ring, u
     }
     uint32_t dst = res + (uint32_t)((rl * nseg + seg) * 8);
     int row = rl;
+    // The three warp sums of a row are issued after its IDPs and stored one tile later, behind the next row's IDPs:
+    // in the plain order (sum, move out of the uniform register, combine, store) a tenth of the loop's samples were
+    // waits for the REDUX results.
+    int s0 = 0, s1 = 0, s2 = 0;
+    uint32_t sdst = 0;
+    bool spend = false;
     for (int t = 0; t < ntiles; ++t) {
         mbar_wait(p, full0 + 8 * rp.stage, rp.phase, kDiagRingFull);
         if (ptrace != nullptr && threadIdx.x == 0) {
@@ -262,9 +268,10 @@ __device__ __forceinline__ RingPos consume_sub(const Params &p, uint32_t ring, u
             if (c < kTileTraceMax) ptrace[((size_t)gridDim.x + blockIdx.x) * kTileTraceMax + c] = globaltimer();
             *tile_cnt = c + 1;
         }
-        if (row < nr) {
+        const bool act = row < nr;
+        int acc[6] = {0, 0, 0, 0, 0, 0};
+        if (act) {
             const uint32_t wrow = ring + rp.stage * tile_bytes + unit_off;
-            int acc[6] = {0, 0, 0, 0, 0, 0};
             if (!BOUNDED) {
                 uint4 w[CPL];
 #pragma unroll
@@ -281,19 +288,27 @@ __device__ __forceinline__ RingPos consume_sub(const Params &p, uint32_t ring, u
                     }
                 }
             }
-            const int t0 = __reduce_add_sync(0xffffffffu, acc[0] + acc[1]);
-            const int t1 = __reduce_add_sync(0xffffffffu, acc[2] + acc[3]);
-            const int t2 = __reduce_add_sync(0xffffffffu, acc[4] + acc[5]);
-            if (lane == 0) {
-                const long long tot = (((long long)t2 << 8) + (long long)t1) * 256 + (long long)t0;
-                asm volatile("st.shared.u64 [%0], %1;" ::"r"(dst), "l"(tot) : "memory");
-            }
+        }
+        if (spend && lane == 0) {
+            const long long tot = (((long long)s2 << 8) + (long long)s1) * 256 + (long long)s0;
+            asm volatile("st.shared.u64 [%0], %1;" ::"r"(sdst), "l"(tot) : "memory");
+        }
+        spend = act;
+        sdst = dst;
+        if (act) {
+            s0 = __reduce_add_sync(0xffffffffu, acc[0] + acc[1]);
+            s1 = __reduce_add_sync(0xffffffffu, acc[2] + acc[3]);
+            s2 = __reduce_add_sync(0xffffffffu, acc[4] + acc[5]);
         }
         dst += 8 * 8;
         row += tr;
         __syncwarp();
         if (lane == 0) mbar_arrive(empty0 + 8 * rp.stage);
         rp.advance(stages);
+    }
+    if (spend && lane == 0) {
+        const long long tot = (((long long)s2 << 8) + (long long)s1) * 256 + (long long)s0;
+        asm volatile("st.shared.u64 [%0], %1;" ::"r"(sdst), "l"(tot) : "memory");
     }
     return rp;
 }
