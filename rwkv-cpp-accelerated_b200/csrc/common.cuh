@@ -76,6 +76,7 @@ struct Params {
     int issue_gap;          // minimum SM cycles between two bulk-copy issues of the producer (0 = unpaced)
     int window;             // bulk copies in flight per CTA (<= stages)
     int cluster;            // CTAs per thread-block cluster (1, 2 or 4): they split the gather and write each other's limb planes
+    int vseg;               // segments per ffn-V row (4E/G bytes): 4, 2 or 1 so that a segment is <= E bytes and a tile 8 / vseg rows
     int bwindow;            // bulk copies in flight per CTA while the consumers exchange vectors (latency of their loads)
     int pf_dist;            // tiles the L2 prefetch cursor runs ahead of the ring (0 = no L2 prefetch)
     int dbg;                // debug experiments (bit 0: run the slice statistics twice, cold / warm code)

@@ -373,6 +373,7 @@ int do_load(M *m, const char *path, int quiet) {
     p.poll_first = 2;
     p.pf_dist = 4;
     p.bwindow = 1;
+    p.vseg = G >= 4 ? 1 : G >= 2 ? 2 : 4; // 4E/G bytes per ffn-V row in segments of at most E bytes
     p.cluster = 1;
     if (p.stages < 2) return fail(5, "n_embed=%llu leaves no room for a two-stage ring", E);
     if (!grid_fits(E, Er, Vr, m->grid)) return fail(5, "a grid of %d CTAs does not fit n_embed=%llu", m->grid, E);

@@ -105,7 +105,7 @@ __device__ __forceinline__ void load_sub(const Params &p, const Slices &sl, Tile
     case 3: c.N = Er; c.tr = 8; c.nr = sl.ne; c.base = p.wo + mc + (size_t)sl.e0 * Er; break;
     case 4: c.N = E; c.tr = 8; c.nr = sl.nk; c.base = p.wfk + 4 * mc + (size_t)sl.k0 * E; break; // ffn K before ffn R
     case 5: c.N = E; c.tr = 8; c.nr = sl.nc; c.base = p.wfr + mc + (size_t)sl.c0 * E; break;
-    default: c.N = 4 * Er; c.tr = 2; c.nr = sl.ne; c.base = p.wfv + 4 * mc + (size_t)sl.e0 * 4 * Er; break;
+    default: c.N = 4 * Er; c.tr = 8 / p.vseg; c.nr = sl.ne; c.base = p.wfv + 4 * mc + (size_t)sl.e0 * 4 * Er; break;
     }
 }
 // The tile under the cursor, then advance. Returns false at the end of the token's schedule.
@@ -221,7 +221,7 @@ __device__ __forceinline__ void dot_chunk(const uint4 w, const uint4 a0, const u
 
 // Consumer side of one streamed sub-matrix: warp w takes unit w of every tile. All arguments are plain
 // values in registers (the hot loop takes them through opaque()).
-// N: bytes per row; nseg: segments per row (1 or 4); planes: shared address of limb plane 0 of this sub's
+// N: bytes per row; nseg: segments per row (1, 2 or 4; a tile is 8 / nseg rows); planes: shared address of limb plane 0 of this sub's
 // activation vector (planes 1, 2 at +N, +2N); res: shared address of this sub's int64 [row][nseg] totals.
 // CPL: 16-byte chunks per lane that hold the limbs of one segment (N / nseg <= CPL * 512).
 // BOUNDED = false: the segment is exactly CPL * 512 bytes - straight-line code, no predicates.
@@ -231,10 +231,11 @@ template <int CPL, bool BOUNDED>
 __device__ __forceinline__ RingPos consume_sub(const Params &p, uint32_t ring, uint32_t full0, uint32_t empty0, uint32_t tile_bytes,
                                                uint32_t stages, uint32_t planes, uint32_t res, int N, int nseg, int nr, RingPos rp,
                                                int warp, int lane, unsigned long long *ptrace, int *tile_cnt) {
-    const int tr = nseg == 4 ? 2 : 8; // rows per tile
-    const int seg_len = nseg == 4 ? N >> 2 : N;
+    const int tr = nseg == 4 ? 2 : nseg == 2 ? 4 : 8; // rows per tile
+    const int seg_len = nseg == 4 ? N >> 2 : nseg == 2 ? N >> 1 : N;
     const int nchunks = seg_len >> 4;
-    const int seg = nseg == 4 ? (warp & 3) : 0, rl = nseg == 4 ? (warp >> 2) : warp; // this warp's unit inside every tile
+    // this warp's unit inside every tile: (row warp / nseg, segment warp % nseg)
+    const int seg = nseg == 4 ? (warp & 3) : nseg == 2 ? (warp & 1) : 0, rl = nseg == 4 ? (warp >> 2) : nseg == 2 ? (warp >> 1) : warp;
     const uint32_t unit_off = (uint32_t)(rl * N + seg * seg_len + lane * 16);
     const int ntiles = (nr + tr - 1) / tr;
     if (ntiles <= 0) return rp;
@@ -1019,7 +1020,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_token(const __grid_constant__ P
         case 1: nvec = 1; N = Er; nseg = 1; nsub = 1; nr0 = ne; tag = ep; break;              // out-proj
         case 2: nvec = 2; N = E; nseg = 1; nsub = 1; nr0 = nk; sub0 = 1; tag = ep; break;     // ffn K (input vector 1 of the gather)
         case 3: nvec = 0; N = E; nseg = 1; nsub = 1; nr0 = nc; tag = ep; break;               // ffn R (input vector 0, already quantised)
-        case 4: nvec = 1; N = 4 * Er; nseg = 4; nsub = 1; nr0 = ne; tag = ep; break;          // ffn V
+        case 4: nvec = 1; N = 4 * Er; nseg = p.vseg; nsub = 1; nr0 = ne; tag = ep; break;     // ffn V: rows of 4E/G bytes in segments of <= E
         default: nvec = 1; N = E; nseg = 1; nsub = 1; nr0 = sl.nv; tag = p.tk; break;         // head
         }
         const float *vec = reinterpret_cast<const float *>(xl + p.off_vec[xi]);
@@ -1063,7 +1064,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_token(const __grid_constant__ P
             ++gk;
         }
         {
-            const bool exact = FULL && N == (nseg == 4 ? 4 * E : E); // segment == CPL * 512 bytes
+            const bool exact = FULL && N == nseg * E; // segment == CPL * 512 bytes
             // results: [sub][row]; ffn K's rows sit behind ffn R's (phase 3 fills those while phase 2's are read)
             uint32_t planes = c_planes + (uint32_t)(sub0 * 3 * N), res = c_res + (uint32_t)(sub0 * nc) * 8u;
             for (int s = 0; s < nsub; ++s) {
@@ -1176,7 +1177,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_token(const __grid_constant__ P
         } else if (ph == 4) {
             // ======== residual (rwkv.cu:574-577), then the next layer's LN1 (or LN_out) ====================
             if (owner_warps) {
-                double part = mine ? sm.scal[0] * row_total(0, ctid, 4) + sm.scal[3] : 0.0;
+                double part = mine ? sm.scal[0] * row_total(0, ctid, p.vseg) + sm.scal[3] : 0.0;
                 float sr = 0.0f;
                 if (multi) {
                     part = peer_sum(p, p.off_in[1], j, part, mine, ep, (unsigned int)l);
