@@ -231,11 +231,12 @@ template <int CPL, bool BOUNDED>
 __device__ __forceinline__ RingPos consume_sub(const Params &p, uint32_t ring, uint32_t full0, uint32_t empty0, uint32_t tile_bytes,
                                                uint32_t stages, uint32_t planes, uint32_t res, int N, int nseg, int nr, RingPos rp,
                                                int warp, int lane, unsigned long long *ptrace, int *tile_cnt) {
-    const int tr = nseg == 4 ? 2 : nseg == 2 ? 4 : 8; // rows per tile
-    const int seg_len = nseg == 4 ? N >> 2 : nseg == 2 ? N >> 1 : N;
+    const int sh = nseg >> 1;    // log2(nseg) for nseg = 1, 2, 4
+    const int tr = 8 >> sh;      // rows per tile
+    const int seg_len = N >> sh;
     const int nchunks = seg_len >> 4;
     // this warp's unit inside every tile: (row warp / nseg, segment warp % nseg)
-    const int seg = nseg == 4 ? (warp & 3) : nseg == 2 ? (warp & 1) : 0, rl = nseg == 4 ? (warp >> 2) : nseg == 2 ? (warp >> 1) : warp;
+    const int seg = warp & (nseg - 1), rl = warp >> sh;
     const uint32_t unit_off = (uint32_t)(rl * N + seg * seg_len + lane * 16);
     const int ntiles = (nr + tr - 1) / tr;
     if (ntiles <= 0) return rp;
