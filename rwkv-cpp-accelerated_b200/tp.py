@@ -26,6 +26,15 @@ def cta_slices(n_embed, world, rank, grid=148, vocab=50277):
     return split(n_embed), split(er), split(4 * er), split(v1 - v0)
 
 
+def ffn_v_tiling(n_embed, world):
+    """(segments per ffn-V row, rows per tile, bytes per tile) on one rank - the arithmetic of `Params::vseg`
+    (engine.cu) and `load_sub` / `consume_sub` (csrc/token_kernel.cuh). A rank's ffn-V rows are 4E/G bytes; they are
+    cut into 4, 2, 1 segments of at most E bytes for G = 1, 2, >= 4, and a tile (eight warp units) is 8 / segments rows."""
+    seg = 1 if world >= 4 else 2 if world >= 2 else 4
+    rows = 8 // seg
+    return seg, rows, rows * (4 * n_embed // world)
+
+
 def weight_bytes_per_rank(n_layers, n_embed, world, rank, vocab=50277):
     """uint8 weight bytes rank `rank` streams per token: 13 L E^2 / G + its vocabulary rows."""
     v0, v1 = shard(vocab, world, rank)

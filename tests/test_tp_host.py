@@ -41,6 +41,20 @@ def test_shards_and_slices_cover_everything_once(tp, n_embed, world):
     assert sum(tp.weight_bytes_per_rank(L, n_embed, world, r) for r in range(world)) == 13 * L * n_embed ** 2 + vocab * n_embed
 
 
+@pytest.mark.parametrize("n_embed", [768, 2048, 4096, 5120])
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_ffn_v_tiles_fit_the_ring_and_the_limb_registers(tp, n_embed, world):
+    """A unit (one warp's share of a tile) is a row segment of at most E bytes - the limbs of E bytes are what a warp
+    holds in registers - and a tile never exceeds the ring stage of 8 x E bytes; up to four ranks it fills it."""
+    seg, rows, tile = tp.ffn_v_tiling(n_embed, world)
+    row_bytes = 4 * n_embed // world
+    assert seg * rows == 8
+    assert row_bytes % seg == 0 and row_bytes // seg <= n_embed
+    assert tile <= 8 * n_embed
+    if world <= 4:
+        assert tile == 8 * n_embed
+
+
 def _worker(rank, world, port, q):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
